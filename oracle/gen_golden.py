@@ -1,0 +1,132 @@
+"""Generate tests/golden/*.pt by executing the REAL reference (build container only).
+
+    python -m oracle.gen_golden
+
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  The fixtures pin ``oracle/cunet_oracle.py`` and
+``oracle/quantize_oracle.py`` to the reference's own behaviour (the reference ships no golden
+vectors).
+"""
+import os
+import sys
+import warnings
+
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader, cunet_oracle, synthetic  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def run_reference(net, img, hm, train=True):
+    net.train(train)
+    net.zero_grad()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if train:
+            outs = net(img)
+            loss = cunet_oracle.multi_loss_mse(outs, hm)
+            loss.backward()
+        else:
+            with torch.no_grad():
+                outs = net(img)
+                loss = cunet_oracle.multi_loss_mse(outs, hm)
+    return outs, loss
+
+
+def tiny_case(name, layer_num, order, loss_num, class_num, neck, growth, c0, seed):
+    """Small-channel configuration: full tensors are stored."""
+    torch.manual_seed(seed)
+    net = ref_loader.create_reference_net(class_num, layer_num, order, loss_num,
+                                          neck_size=neck, growth_rate=growth, init_chan_num=c0)
+    state0 = {k: v.clone() for k, v in net.state_dict().items()}
+    gen = torch.Generator().manual_seed(seed + 1)
+    img = torch.rand(2, 3, 64, 64, generator=gen)
+    hm = torch.rand(2, class_num, 16, 16, generator=gen)
+    outs, loss = run_reference(net, img, hm, train=True)
+    grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in net.named_parameters()}
+    state1 = {k: v.clone() for k, v in net.state_dict().items()}
+    outs_eval, loss_eval = run_reference(net, img, hm, train=False)
+    torch.save({
+        "config": dict(class_num=class_num, layer_num=layer_num, order=order, loss_num=loss_num,
+                       neck_size=neck, growth_rate=growth, init_chan_num=c0),
+        "state_before": state0, "img": img, "heatmap": hm,
+        "outputs_train": [o.detach() for o in outs], "loss_train": loss.detach(),
+        "grads": grads, "state_after_train": state1,
+        "outputs_eval": [o.detach() for o in outs_eval], "loss_eval": loss_eval.detach(),
+    }, os.path.join(OUT, name))
+
+
+def real_case(name, layer_num, order, loss_num, class_num, n, seed):
+    """Real channel configuration (4/32/128): digests only (weights are re-derivable from
+    cunet_oracle.init_state(seed), inputs from synthetic.make_inputs(seed))."""
+    state = cunet_oracle.init_state(class_num, layer_num, order, seed=seed)
+    net = ref_loader.create_reference_net(class_num, layer_num, order, loss_num)
+    missing = net.load_state_dict(state, strict=True)
+    img, hm = synthetic.make_inputs(n, class_num, seed=seed)
+    outs, loss = run_reference(net, img, hm, train=True)
+    sd = net.state_dict()
+    digest = {
+        "config": dict(class_num=class_num, layer_num=layer_num, order=order, loss_num=loss_num,
+                       n=n, seed=seed),
+        "state_keys": list(sd.keys()),
+        "state_shapes": [tuple(v.shape) for v in sd.values()],
+        "loss_train": loss.detach(),
+        "out_samples": [o.detach()[:, ::7, ::5, ::3].clone() for o in outs],
+        "out_absmax": [o.detach().abs().max() for o in outs],
+        "grad_norms": {k: p.grad.norm().clone() for k, p in net.named_parameters() if p.grad is not None},
+        "grad_samples": {k: p.grad.flatten()[::97].clone() for k, p in net.named_parameters() if p.grad is not None},
+        "running_mean_samples": {k: v.flatten()[::13].clone() for k, v in sd.items()
+                                 if k.endswith("running_mean")},
+        "running_var_samples": {k: v.flatten()[::13].clone() for k, v in sd.items()
+                                if k.endswith("running_var")},
+        "num_batches_tracked": {k: int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")},
+    }
+    outs_eval, loss_eval = run_reference(net, img, hm, train=False)
+    digest["loss_eval"] = loss_eval.detach()
+    digest["out_eval_samples"] = [o.detach()[:, ::7, ::5, ::3].clone() for o in outs_eval]
+    torch.save(digest, os.path.join(OUT, name))
+
+
+def quant_case(name, bits_w, seed):
+    """Run the real utils/quantize.py QuanOp on a small stack of Conv2d modules."""
+    q = ref_loader.load_reference_quantize(bits_w)
+    gen = torch.Generator().manual_seed(seed)
+    shapes = [(8, 3, 3, 3), (32, 128, 3, 3), (16, 40, 1, 1), (32, 128, 3, 3), (5, 16, 1, 1), (4, 4, 1, 1)]
+    convs = []
+    for co, ci, k, _ in shapes:
+        m = nn.Conv2d(ci, co, k, bias=False)
+        m.weight.data = (torch.rand(co, ci, k, k, generator=gen) * 2 - 1) * 1.5
+        convs.append(m)
+    model = nn.Sequential(*convs)
+    w0 = [m.weight.data.clone() for m in convs]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        op = q.QuanOp(model)
+        op.quantization()
+        wq = [m.weight.data.clone() for m in convs]
+        grads = [torch.randn(m.weight.shape, generator=gen) * 0.01 for m in convs]
+        for m, g in zip(convs, grads):
+            m.weight.grad = g.clone()
+        op.restore()
+        wr = [m.weight.data.clone() for m in convs]
+        op.updateQuanGradWeight()
+        gq = [m.weight.grad.clone() for m in convs]
+    torch.save({"bits_w": bits_w, "bits_g": 8, "w0": w0, "wq": wq, "wr": wr, "g0": grads, "gq": gq,
+                "num_targets": op.num_of_params}, os.path.join(OUT, name))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    tiny_case("tiny_L3_K2.pt", 3, 2, 2, 5, 2, 8, 16, seed=11)
+    tiny_case("tiny_L2_K1.pt", 2, 1, 2, 3, 4, 8, 16, seed=12)
+    tiny_case("tiny_L3_K0.pt", 3, 0, 3, 4, 2, 8, 16, seed=13)
+    real_case("real_L2_K1_C68_n1.pt", 2, 1, 2, 68, 1, seed=0)
+    for bw in (1, 2, 8):
+        quant_case("quanop_bits%d.pt" % bw, bw, seed=20 + bw)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
