@@ -1,0 +1,12 @@
+"""cu-net_b200: B200-native (sm_100a) implementation of the CU-Net training/inference hot path.
+
+Layout
+  csrc/        hand-written CUDA kernels + the C ABI (include/cunet_b200.h) -> libcunet_b200.so
+  lib.py       ctypes binding of the C ABI (fails loudly when the library is missing)
+  plan.py      static op plan of the network (virtual-concat segment tables, buffers, schedules)
+  engine.py    executes a plan through the C ABI (forward, backward, fused train step)
+  models/      drop-in for the reference's models/cu_net.py  (create_cu_net)
+  utils/       drop-in for utils/quantize.py (QuanOp), BinOp
+  pylib/       drop-in for pylib/Evaluation.get_preds
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,356 @@
+// Fused  virtual-concat -> BatchNorm -> ReLU -> conv (1x1 | 3x3)  [-> maxpool 2x2]  forward, sm_100a.
+//
+// Replaces, per call, the reference's torch.cat + nn.BatchNorm2d + nn.ReLU + nn.Conv2d (+ nn.MaxPool2d)
+// sequence (models/cu_net.py:11-17, 22-25, 41-48, 195-198, 249, 260).
+//
+// GEMM view: D[128 pixels][CoutPad] = A[128 pixels][K] * W^T, K = taps * CinPad.
+//   A operand : gathered from <= 8 source tensors (no cat tensor exists), BN scale/shift + ReLU applied
+//               on the fly by 8 loader warps (global -> registers -> swizzled smem row tile).
+//               Nearest-x2 upsample of a source = index math in the gather (models/cu_net.py:250,265).
+//   B operand : pre-packed weight image, one 1-D TMA bulk copy per K block.
+//   MMA       : tcgen05.mma cta_group::1, kind::f16 (bf16) or kind::tf32, M=128, N=CoutPad, fp32 accum in TMEM.
+//   Epilogue  : TMEM -> smem (fp32) -> {round to storage dtype, optional 2x2 maxpool + argmax index,
+//               per-channel sum / sum-of-squares for the consumers' BatchNorm} -> global (coalesced).
+//
+// Warp roles (320 threads): warps 0-7 A loaders then epilogue, warp 8 weight-copy producer,
+// warp 9 TMEM allocator + MMA issuer.  3-stage mbarrier ring; 2 CTAs / SM.
+#include "common.cuh"
+#include "../../include/cunet_b200.h"
+#include "host_util.h"
+
+namespace cunet {
+
+constexpr int FWD_STAGES = 3;
+constexpr int FWD_STAGE_BYTES = 32768;  // 16 KB A tile + 16 KB B tile
+constexpr int FWD_THREADS = 320;
+constexpr int MAX_CIN = 512;
+
+struct FwdSmemTail {
+  uint64_t full[FWD_STAGES];
+  uint64_t empty[FWD_STAGES];
+  uint64_t accum;
+  uint32_t tmem_base;
+  int seg_start[CUNET_MAX_SEG + 1];
+  float scale[MAX_CIN];
+  float shift[MAX_CIN];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_constant__ cunet_conv_fwd_params p) {
+  using E = Elem<T>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  FwdSmemTail* tail = reinterpret_cast<FwdSmemTail*>(smem + FWD_STAGES * FWD_STAGE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int grouped = p.pool;
+
+  int Cin = 0;
+  for (int s = 0; s < p.nseg; ++s) Cin += p.seg[s].C;
+  const int nkb = (Cin + E::KBE - 1) / E::KBE;  // K blocks per tap
+  const int nsteps = p.taps * nkb;
+  const uint32_t tmem_cols = p.CoutPad <= 32 ? 32 : (p.CoutPad <= 64 ? 64 : 128);
+
+  // ---------------------------------------------------------------- one-time setup
+  if (tid == 0) {
+    int acc = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      tail->seg_start[s] = acc;
+      acc += p.seg[s].C;
+    }
+    for (int s = p.nseg; s <= CUNET_MAX_SEG; ++s) tail->seg_start[s] = acc;
+    for (int s = 0; s < FWD_STAGES; ++s) {
+      mbar_init(&tail->full[s], 9);   // 8 loader warps + the producer's expect_tx arrive
+      mbar_init(&tail->empty[s], 1);  // one tcgen05.commit
+    }
+    mbar_init(&tail->accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&tail->tmem_base, tmem_cols);
+  // BN coefficients of this op's BatchNorm (nn.BatchNorm2d: biased batch variance in train mode)
+  for (int k = tid; k < nkb * E::KBE; k += FWD_THREADS) {
+    float sc = 0.f, sh = 0.f;
+    if (k < Cin) {
+      double mean, var;
+      if (p.bn_train) {
+        int s = 0, base = 0;
+        while (s + 1 < p.nseg && k >= base + p.seg[s].C) {
+          base += p.seg[s].C;
+          ++s;
+        }
+        const int c = k - base;
+        const double su = p.seg[s].stats[c], sq = p.seg[s].stats[p.seg[s].C + c];
+        mean = su * p.seg[s].inv_count;
+        var = sq * p.seg[s].inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+      } else {
+        mean = p.rmean[k];
+        var = p.rvar[k];
+      }
+      const double istd = 1.0 / sqrt(var + (double)p.eps);
+      const double g = p.gamma[k];
+      sc = (float)(g * istd);
+      sh = (float)((double)p.beta[k] - mean * g * istd);
+    }
+    tail->scale[k] = sc;
+    tail->shift[k] = sh;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  PixGeom geom;
+  geom.N = p.N; geom.H = p.H; geom.W = p.W; geom.M = p.N * p.H * p.W;
+
+  if (warp < 8) {
+    // ============================================================== A loaders
+    const int c = tid & 7;
+    int rn[4], rh[4], rw[4];
+    uint32_t rvalid = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = (tid >> 3) + 32 * q;
+      if (tile_row_pixel(geom, tile, r, grouped, rn[q], rh[q], rw[q])) rvalid |= 1u << q;
+    }
+    uint4 cur[4], nxt[4];
+    uint32_t cmask = 0, nmask = 0;
+
+    auto issue = [&](int it, uint4* dst, uint32_t& mask) {
+      mask = 0;
+      const int tap = it / nkb, kb = it - tap * nkb;
+      const int ch = kb * E::KBE + c * E::EPC;
+      if (ch >= Cin) return;
+      int s = 0;
+      while (ch >= tail->seg_start[s + 1]) ++s;
+      const cunet_seg& sg = p.seg[s];
+      const int local = ch - tail->seg_start[s];
+      int dy = 0, dx = 0;
+      if (p.taps == 9) {
+        dy = tap / 3 - 1;
+        dx = tap - (tap / 3) * 3 - 1;
+      }
+      const char* base = reinterpret_cast<const char*>(sg.ptr) + (size_t)local * E::ESZ;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!((rvalid >> q) & 1)) continue;
+        const int hh = rh[q] + dy, ww = rw[q] + dx;
+        if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+        long row;
+        if (sg.up)
+          row = ((long)rn[q] * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1);
+        else
+          row = ((long)rn[q] * p.H + hh) * p.W + ww;
+        dst[q] = ldg128(base + row * (long)sg.ld * E::ESZ);
+        mask |= 1u << q;
+      }
+    };
+
+    issue(0, cur, cmask);
+    for (int it = 0; it < nsteps; ++it) {
+      const int s = it % FWD_STAGES;
+      const uint32_t ph = (it / FWD_STAGES) & 1;
+      if (it + 1 < nsteps) issue(it + 1, nxt, nmask);
+      mbar_wait(&tail->empty[s], ph ^ 1);
+      const int kb = it % nkb;
+      const int ch = kb * E::KBE + c * E::EPC;
+      float sc[E::EPC], sh[E::EPC];
+#pragma unroll
+      for (int e = 0; e < E::EPC; ++e) {
+        sc[e] = tail->scale[ch + e];
+        sh[e] = tail->shift[ch + e];
+      }
+      const uint32_t abase = smem_u32(smem + s * FWD_STAGE_BYTES);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = (tid >> 3) + 32 * q;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if ((cmask >> q) & 1) {
+          float f[E::EPC];
+          Chunk<T>::unpack(cur[q], f);
+#pragma unroll
+          for (int e = 0; e < E::EPC; ++e) f[e] = fmaxf(fmaf(f[e], sc[e], sh[e]), 0.f);
+          o = Chunk<T>::pack_mma(f);
+        }
+        sts128(abase + tile_off(r, c), o);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->full[s]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+      cmask = nmask;
+    }
+  } else if (warp == 8) {
+    // ============================================================== weight producer (TMA bulk)
+    if (lane == 0) {
+      const uint32_t bbytes = (uint32_t)p.CoutPad * 128u;
+      const char* w = reinterpret_cast<const char*>(p.wpack);
+      for (int it = 0; it < nsteps; ++it) {
+        const int s = it % FWD_STAGES;
+        const uint32_t ph = (it / FWD_STAGES) & 1;
+        mbar_wait(&tail->empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&tail->full[s], bbytes);
+        bulk_g2s(smem + s * FWD_STAGE_BYTES + 16384, w + (size_t)it * bbytes, bbytes, &tail->full[s]);
+      }
+    }
+  } else {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(E::FMT, 128, (uint32_t)p.CoutPad, 0, 0);
+      for (int it = 0; it < nsteps; ++it) {
+        const int s = it % FWD_STAGES;
+        const uint32_t ph = (it / FWD_STAGES) & 1;
+        mbar_wait(&tail->full[s], ph);
+        tc_fence_after();
+        const uint32_t a = smem_u32(smem + s * FWD_STAGE_BYTES);
+        const uint32_t b = a + 16384;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          umma<T>(tmem, make_sdesc(a + kk * 32, 16, 1024), make_sdesc(b + kk * 32, 16, 1024), idesc,
+                  (uint32_t)((it | kk) != 0));
+        }
+        tc_commit(&tail->empty[s]);
+      }
+      tc_commit(&tail->accum);
+    }
+  }
+
+  // ================================================================== epilogue (warps 0-7)
+  const int ld_ep = p.CoutPad + 4;  // fp32 words per staged row (bank-conflict-free float4 rows)
+  float* ep = reinterpret_cast<float*>(smem);
+  float* red = reinterpret_cast<float*>(smem + 128 * (128 + 4) * 4);  // [256][8] partial stats
+  if (warp < 8) {
+    mbar_wait(&tail->accum, 0);
+    tc_fence_after();
+    const int lq = warp & 3, half = warp >> 2;
+    const int row = lq * 32 + lane;
+    const int ncol_half = p.CoutPad >> 1;
+    for (int j = 0; j < ncol_half; j += 8) {
+      float v[8];
+      const int col = half * ncol_half + j;
+      tmem_ld8(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col, v);
+      float4* dst = reinterpret_cast<float4*>(ep + row * ld_ep + col);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp < 8) {
+    const int nq = p.CoutPad >> 2;  // channel quads per row
+    const bool do_stats = p.out_stats != nullptr;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nrows_out = grouped ? 32 : 128;
+    const long rows_total = grouped ? (long)geom.M / 4 : (long)geom.M;
+    for (int idx = tid; idx < nrows_out * nq; idx += 256) {
+      const int r = idx / nq, q = idx - r * nq;
+      const long grow = (long)tile * nrows_out + r;
+      if (grow >= rows_total) continue;
+      float4 v;
+      uint32_t pidx = 0;
+      if (!grouped) {
+        v = *reinterpret_cast<const float4*>(ep + r * ld_ep + 4 * q);
+      } else {
+        // nn.MaxPool2d(2,2): first maximum in row-major window order wins
+        v = *reinterpret_cast<const float4*>(ep + (4 * r) * ld_ep + 4 * q);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          const float4 u = *reinterpret_cast<const float4*>(ep + (4 * r + k) * ld_ep + 4 * q);
+          if (u.x > v.x) { v.x = u.x; pidx = (pidx & ~0xFFu) | (uint32_t)k; }
+          if (u.y > v.y) { v.y = u.y; pidx = (pidx & ~0xFF00u) | ((uint32_t)k << 8); }
+          if (u.z > v.z) { v.z = u.z; pidx = (pidx & ~0xFF0000u) | ((uint32_t)k << 16); }
+          if (u.w > v.w) { v.w = u.w; pidx = (pidx & ~0xFF000000u) | ((uint32_t)k << 24); }
+        }
+      }
+      const int ch = 4 * q;
+      if (ch >= p.Cout && !p.out_fp32) continue;
+      if (p.out_fp32) {
+        if (ch < p.out_ld)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.out_ld + ch) = v;
+      } else {
+        T* o = reinterpret_cast<T*>(p.out) + grow * p.out_ld + ch;
+        T t0 = from_f<T>(v.x), t1 = from_f<T>(v.y), t2 = from_f<T>(v.z), t3 = from_f<T>(v.w);
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(o) = v;
+        } else {
+          uint2 pk;
+          __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+          pk.x = *reinterpret_cast<uint32_t*>(&a);
+          pk.y = *reinterpret_cast<uint32_t*>(&b);
+          *reinterpret_cast<uint2*>(o) = pk;
+        }
+        // statistics of the values as stored (what the consumers will read back)
+        v.x = to_f<T>(t0); v.y = to_f<T>(t1); v.z = to_f<T>(t2); v.w = to_f<T>(t3);
+      }
+      if (grouped && p.pool_idx) *reinterpret_cast<uint32_t*>(p.pool_idx + grow * p.Cout + ch) = pidx;
+      if (do_stats) {
+        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+        s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+      }
+    }
+    if (do_stats) {
+      // host guarantees 256 % nq == 0 when out_stats != NULL -> every thread owns one channel quad
+      float4* rp = reinterpret_cast<float4*>(red + tid * 8);
+      rp[0] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+      rp[1] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    }
+  }
+  __syncthreads();
+  if (warp < 8 && p.out_stats != nullptr && tid < p.Cout) {
+    const int nq = p.CoutPad >> 2;
+    const int q = tid >> 2, e = tid & 3;
+    float a = 0.f, b = 0.f;
+    for (int t = q; t < 256; t += nq) {
+      a += red[t * 8 + e];
+      b += red[t * 8 + 4 + e];
+    }
+    atomicAdd(p.out_stats + tid, (double)a);
+    atomicAdd(p.out_stats + p.Cout + tid, (double)b);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace cunet
+
+using namespace cunet;
+
+extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
+  if (!p) return cunet_fail("conv_fwd: null params");
+  if (p->nseg < 1 || p->nseg > CUNET_MAX_SEG) return cunet_fail("conv_fwd: bad nseg");
+  if (p->taps != 1 && p->taps != 9) return cunet_fail("conv_fwd: taps must be 1 or 9");
+  if (p->CoutPad % 16 || p->CoutPad < 16 || p->CoutPad > 128 || p->Cout > p->CoutPad)
+    return cunet_fail("conv_fwd: CoutPad must be a multiple of 16 in [16,128]");
+  int cin = 0;
+  for (int s = 0; s < p->nseg; ++s) {
+    if (p->seg[s].C % 32) return cunet_fail("conv_fwd: segment channels must be a multiple of 32");
+    if (p->bn_train && !p->seg[s].stats) return cunet_fail("conv_fwd: train-mode BN needs seg stats");
+    cin += p->seg[s].C;
+  }
+  if (cin > MAX_CIN) return cunet_fail("conv_fwd: too many input channels");
+  if (p->out_stats && (256 % (p->CoutPad / 4) || p->Cout != p->CoutPad))
+    return cunet_fail("conv_fwd: out_stats needs Cout == CoutPad in {32, 64, 128}");
+  if (p->pool && ((p->H | p->W) & 1)) return cunet_fail("conv_fwd: pool needs even H, W");
+  if (p->Cout % 4 && !p->out_fp32) return cunet_fail("conv_fwd: Cout must be a multiple of 4");
+  const long M = (long)p->N * p->H * p->W;
+  if (M <= 0) return 0;
+  const long tiles = p->pool ? (M / 4 + 31) / 32 : (M + 127) / 128;
+  const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdSmemTail) + 1024;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (p->dtype == CUNET_BF16) {
+    e = cudaFuncSetAttribute(conv_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd attr", e);
+    conv_fwd_kernel<bf16><<<(unsigned)tiles, FWD_THREADS, smem, st>>>(*p);
+  } else {
+    e = cudaFuncSetAttribute(conv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd attr", e);
+    conv_fwd_kernel<float><<<(unsigned)tiles, FWD_THREADS, smem, st>>>(*p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd launch", e);
+  return 0;
+}

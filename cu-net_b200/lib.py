@@ -1,0 +1,102 @@
+"""ctypes binding of libcunet_b200.so (the C ABI declared in include/cunet_b200.h).
+
+The product has exactly one compute path: these entry points.  If the shared library is missing or
+a call fails, a ``CunetError`` is raised -- there is no CPU / PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcunet_b200.so")
+_lib = None
+
+F32, BF16 = 0, 1
+MAX_SEG = 8
+
+
+class CunetError(RuntimeError):
+    pass
+
+
+class Seg(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("stats", C.c_void_p), ("inv_count", C.c_double),
+                ("C", C.c_int), ("ld", C.c_int), ("up", C.c_int), ("reserved", C.c_int)]
+
+
+class ConvFwdParams(C.Structure):
+    _fields_ = [("seg", Seg * MAX_SEG), ("nseg", C.c_int),
+                ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("rmean", C.c_void_p), ("rvar", C.c_void_p),
+                ("bn_train", C.c_int), ("eps", C.c_float),
+                ("wpack", C.c_void_p), ("Cout", C.c_int), ("CoutPad", C.c_int),
+                ("out", C.c_void_p), ("out_ld", C.c_int), ("out_fp32", C.c_int),
+                ("out_stats", C.c_void_p), ("pool", C.c_int), ("pool_idx", C.c_void_p),
+                ("dtype", C.c_int)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("fwd", C.c_void_p), ("dgrad", C.c_void_p),
+                ("Cout", C.c_int), ("Cin", C.c_int), ("taps", C.c_int), ("CoutPad", C.c_int)]
+
+
+def load():
+    """Load the shared library (idempotent).  Raises CunetError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CunetError("libcunet_b200.so not found at %s -- run `python __graft_entry__.py` "
+                         "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.cunet_last_error.restype = C.c_char_p
+    lib.cunet_abi_version.restype = C.c_int
+    lib.cunet_pack_fwd_bytes.restype = C.c_long
+    lib.cunet_pack_fwd_bytes.argtypes = [C.c_int] * 4
+    lib.cunet_pack_dgrad_bytes.restype = C.c_long
+    lib.cunet_pack_dgrad_bytes.argtypes = [C.c_int] * 4
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise CunetError("libcunet_b200.so does not export %s (stale build?)" % name)
+    _lib = lib
+    return lib
+
+
+# every symbol include/cunet_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "cunet_last_error", "cunet_abi_version",
+    "cunet_conv_fwd", "cunet_pack_weights", "cunet_pack_fwd_bytes", "cunet_pack_dgrad_bytes",
+]
+
+
+def check(rc, what):
+    if rc != 0:
+        raise CunetError("%s failed (%d): %s" % (what, rc, load().cunet_last_error().decode()))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dptr(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def conv_fwd(params):
+    check(load().cunet_conv_fwd(C.byref(params), stream_ptr()), "cunet_conv_fwd")
+
+
+def pack_weights(descs_dev_ptr, ndesc, dtype):
+    check(load().cunet_pack_weights(C.c_void_p(descs_dev_ptr), C.c_int(ndesc), C.c_int(dtype), C.c_int(0),
+                                    stream_ptr()), "cunet_pack_weights")
+
+
+def pack_fwd_bytes(cin, taps, cout_pad, dtype):
+    return int(load().cunet_pack_fwd_bytes(cin, taps, cout_pad, dtype))
+
+
+def pack_dgrad_bytes(cin, taps, cout_pad, dtype):
+    return int(load().cunet_pack_dgrad_bytes(cin, taps, cout_pad, dtype))

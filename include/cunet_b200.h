@@ -1,0 +1,90 @@
+/* cunet_b200.h -- C ABI of libcunet_b200.so, the sm_100a kernel library behind the CU-Net hot path.
+ *
+ * The reference (zhiqiangdon/CU-Net) has no FFI: its "lower layer" is PyTorch library calls made from
+ * models/cu_net.py, cu-net.py, utils/quantize.py and pylib/Evaluation.py.  Each entry point below
+ * replaces one group of those calls (reference file:line cited per function).  Conventions:
+ *   - plain pointers and sizes, no torch types; every pointer is a DEVICE pointer unless stated;
+ *   - the caller allocates every buffer, including workspaces;
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*), no internal synchronisation, no host
+ *     callbacks => CUDA-graph capturable;
+ *   - return 0 on success, <0 on error; cunet_last_error() returns a thread-local message;
+ *   - activations are NHWC ("pixel rows"): tensor [N*H*W][ld] of dtype CUNET_F32 / CUNET_BF16;
+ *   - weights / gradients visible to the caller keep the reference layout [Cout][Cin][kh][kw] fp32.
+ */
+#ifndef CUNET_B200_H_
+#define CUNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUNET_F32 0
+#define CUNET_BF16 1
+#define CUNET_MAX_SEG 8
+
+const char* cunet_last_error(void);
+int cunet_abi_version(void);
+
+/* One source tensor of a virtual channel concat (torch.cat(inputs, 1), models/cu_net.py:13). */
+typedef struct {
+  const void* ptr;     /* [rows][ld] activations                                                   */
+  const double* stats; /* [2*C]: per-channel sum, sum of squares of this tensor (train-mode BN)    */
+  double inv_count;    /* 1 / (rows of this tensor) -- elements per channel                        */
+  int C;               /* channels of this segment (multiple of 32)                                */
+  int ld;              /* row stride in elements                                                    */
+  int up;              /* 1: tensor is at half resolution; nearest x2 upsample fused (cu_net.py:250,265) */
+  int reserved;
+} cunet_seg;
+
+/* Fused  cat -> BatchNorm -> ReLU -> conv(1x1 | 3x3 pad 1)  [-> 2x2 maxpool]  forward.
+ * Replaces _bn_function_factory + nn.Conv2d (models/cu_net.py:11-17, 24, 43, 47-48, 197) and the
+ * nn.MaxPool2d that follows a down-block's adapters_ahead (models/cu_net.py:249, 260).
+ * Epilogue also accumulates the per-channel sum / sum-of-squares of the tensor it writes, which is the
+ * batch statistic every consumer BatchNorm of that tensor needs (nn.BatchNorm2d train mode). */
+typedef struct {
+  cunet_seg seg[CUNET_MAX_SEG];
+  int nseg;
+  int N, H, W;        /* output resolution (before the optional pool) */
+  int taps;           /* 1 (1x1) or 9 (3x3, pad 1)                     */
+  const float* gamma; /* [Cin] BN weight, concat order                 */
+  const float* beta;  /* [Cin] BN bias                                 */
+  const float* rmean; /* [Cin] running mean  (eval mode)               */
+  const float* rvar;  /* [Cin] running var   (eval mode)               */
+  int bn_train;       /* 1: batch statistics from seg[].stats; 0: running statistics */
+  float eps;
+  const void* wpack;  /* packed weights from cunet_pack_weights (fwd image) */
+  int Cout, CoutPad;  /* CoutPad: multiple of 16, <= 128              */
+  void* out;          /* [rows][out_ld]                                */
+  int out_ld;
+  int out_fp32;       /* 1: store fp32 regardless of dtype (heatmap heads) */
+  double* out_stats;  /* [2*Cout] accumulated (+=) or NULL             */
+  int pool;           /* 1: write maxpool2x2(out) [N*H/2*W/2][out_ld] + pool_idx */
+  uint8_t* pool_idx;  /* [N*H/2*W/2][Cout] argmax position (dy*2+dx) or NULL */
+  int dtype;          /* CUNET_F32 (tf32 MMA) or CUNET_BF16           */
+} cunet_conv_fwd_params;
+
+int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream);
+
+/* Weight packing: reference-layout fp32 master weights -> tensor-core operand images.
+ * One descriptor per conv; all descriptors processed by one launch.
+ *   fwd image  : [tap][kb][CoutPad rows][128 B]  K = input channel  (B operand of the forward GEMM)
+ *   dgrad image: [chunk][kb][128 rows][128 B]    rows = input channel, K = (tap, output channel)
+ */
+typedef struct {
+  const float* w;  /* [Cout][Cin][k][k] fp32                               */
+  void* fwd;       /* fwd image or NULL                                     */
+  void* dgrad;     /* dgrad image or NULL                                   */
+  int Cout, Cin, taps, CoutPad;
+} cunet_pack_desc;
+
+int cunet_pack_weights(const cunet_pack_desc* descs_dev, int ndesc, int dtype, int max_chunks, void* stream);
+/* bytes of the images for one conv */
+long cunet_pack_fwd_bytes(int Cin, int taps, int CoutPad, int dtype);
+long cunet_pack_dgrad_bytes(int Cin, int taps, int CoutPad, int dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUNET_B200_H_ */

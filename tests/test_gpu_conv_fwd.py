@@ -1,0 +1,126 @@
+"""GPU parity of the fused cat->BN->ReLU->conv forward kernel (cunet_conv_fwd) through the C ABI."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests import ops_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(lib, dtype):
+    return torch.bfloat16 if dtype == lib.BF16 else torch.float32
+
+
+def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=True, out_fp32=False,
+                 cout_pad=None, seed=0):
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    td = _mk(lib, dtype)
+    cout_pad = cout_pad or cout
+    srcs, stats, counts = [], [], []
+    for c, up in zip(seg_c, ups):
+        hh, ww = (h // 2, w // 2) if up else (h, w)
+        x = (torch.randn(n * hh * ww, c, generator=g) * 1.3 + 0.4).to(dev).to(td)
+        srcs.append(x)
+        stats.append(ops_ref.tensor_stats(x))
+        counts.append(n * hh * ww)
+    cin = sum(seg_c)
+    gamma = torch.rand(cin, generator=g).to(dev)
+    beta = (torch.randn(cin, generator=g) * 0.2).to(dev)
+    rmean = (torch.randn(cin, generator=g) * 0.3).to(dev)
+    rvar = (torch.rand(cin, generator=g) + 0.5).to(dev)
+    k = 3 if taps == 9 else 1
+    weight = ((torch.rand(cout, cin, k, k, generator=g) * 2 - 1) / (cin * k * k) ** 0.5).to(dev)
+
+    # pack weights through the ABI
+    nbytes = lib.pack_fwd_bytes(cin, taps, cout_pad, dtype)
+    wpack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    desc = lib.PackDesc(weight.data_ptr(), wpack.data_ptr(), None, cout, cin, taps, cout_pad)
+    desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).to(dev)
+    lib.pack_weights(desc_dev.data_ptr(), 1, dtype)
+
+    rows_out = n * h * w // (4 if pool else 1)
+    out_ld = cout_pad if out_fp32 else cout
+    out = torch.full((rows_out, out_ld), float("nan"), device=dev, dtype=torch.float32 if out_fp32 else td)
+    out_stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if not out_fp32 else None
+    pidx = torch.zeros(rows_out, cout, dtype=torch.uint8, device=dev) if pool else None
+
+    p = lib.ConvFwdParams()
+    p.nseg = len(srcs)
+    for i, (x, st, cnt, up) in enumerate(zip(srcs, stats, counts, ups)):
+        p.seg[i].ptr = x.data_ptr()
+        p.seg[i].stats = st.data_ptr()
+        p.seg[i].inv_count = 1.0 / cnt
+        p.seg[i].C = x.shape[1]
+        p.seg[i].ld = x.shape[1]
+        p.seg[i].up = int(up)
+    p.N, p.H, p.W, p.taps = n, h, w, taps
+    p.gamma, p.beta, p.rmean, p.rvar = gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr()
+    p.bn_train, p.eps = int(train), 1e-5
+    p.wpack, p.Cout, p.CoutPad = wpack.data_ptr(), cout, cout_pad
+    p.out, p.out_ld, p.out_fp32 = out.data_ptr(), out_ld, int(out_fp32)
+    p.out_stats = out_stats.data_ptr() if out_stats is not None else None
+    p.pool = int(pool)
+    p.pool_idx = pidx.data_ptr() if pidx is not None else None
+    p.dtype = dtype
+    lib.conv_fwd(p)
+    torch.cuda.synchronize()
+
+    # reference (fp32 on the same device, same rounded inputs)
+    if train:
+        scale, shift, _, _ = ops_ref.bn_coeffs(stats, counts, gamma, beta)
+    else:
+        istd = 1.0 / torch.sqrt(rvar.double() + 1e-5)
+        scale = (gamma.double() * istd).float()
+        shift = (beta.double() - rmean.double() * gamma.double() * istd).float()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref, ridx = ops_ref.conv_fwd_ref([s.float() for s in srcs], ups, n, h, w, scale, shift, weight, pool)
+    return out, ref, out_stats, pidx, ridx
+
+
+def _relerr(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()
+
+
+CASES = [
+    # (name, n,h,w, seg_c, ups, cout, taps, pool, train, out_fp32, cout_pad)
+    ("1x1_128", 2, 16, 16, [128], [0], 128, 1, False, True, False, None),
+    ("1x1_160_multi", 2, 16, 16, [128, 32], [0, 0], 128, 1, False, True, False, None),
+    ("1x1_192_pool", 2, 16, 16, [128, 32, 32], [0, 0, 0], 128, 1, True, True, False, None),
+    ("1x1_320_up", 2, 16, 16, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, False, True, False, None),
+    ("3x3", 2, 16, 16, [128], [0], 32, 9, False, True, False, None),
+    ("3x3_small", 3, 4, 4, [128], [0], 32, 9, False, True, False, None),
+    ("head68", 2, 16, 16, [128], [0], 68, 1, False, True, True, 80),
+    ("head16_eval", 1, 8, 8, [128], [0], 16, 1, False, False, True, 16),
+    ("1x1_tail", 3, 4, 4, [128, 32], [0, 0], 128, 1, False, True, False, None),
+    ("1x1_pool_tail", 3, 4, 4, [128, 32, 32], [0, 0, 0], 128, 1, True, True, False, None),
+    ("1x1_big", 4, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, False, True, False, None),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_conv_fwd(case, dtype_name):
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.F32 if dtype_name == "f32" else lib.BF16
+    name, n, h, w, seg_c, ups, cout, taps, pool, train, out_fp32, cout_pad = case
+    out, ref, out_stats, pidx, ridx = run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool, train,
+                                                    out_fp32, cout_pad)
+    got = out.float()[:, :cout]
+    assert torch.isfinite(got).all(), "kernel left unwritten / non-finite outputs"
+    err = _relerr(got, ref)
+    tol = 2e-3 if dtype == lib.F32 else 1.5e-2      # tf32 operands / bf16 operands+storage
+    assert err < tol, "%s %s rel err %g" % (name, dtype_name, err)
+    if out_fp32 and cout_pad and cout_pad > cout:
+        assert (out[:, cout:] == 0).all()
+    if out_stats is not None:
+        st_ref = ops_ref.tensor_stats(got)
+        assert _relerr(out_stats, st_ref) < 1e-4
+    if pool:
+        # argmax positions must agree wherever the maximum is not a (near) tie
+        agree = (pidx == ridx).float().mean().item()
+        assert agree > (0.999 if dtype == lib.F32 else 0.97), agree
