@@ -162,6 +162,23 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c) {
   return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
 }
 
+// MN-major operands (wgrad).  16-bit types use the same SWIZZLE_128B image as above.  32-bit types (tf32)
+// need SWIZZLE_128B_BASE32B (layout_type 1): the swizzle permutes 32-byte units with (row & 3) and the K
+// atom is 4 rows, SBO = stride between 4-row groups (measured with tools/umma_probe.cu on B200; the other
+// layout types return zeros for MN-major tf32).
+template <typename T> __device__ __forceinline__ uint32_t tile_off_mn(int r, int c);
+template <> __device__ __forceinline__ uint32_t tile_off_mn<bf16>(int r, int c) { return tile_off(r, c); }
+template <> __device__ __forceinline__ uint32_t tile_off_mn<float>(int r, int c) {
+  return (uint32_t)(r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4));
+}
+template <typename T> __device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_bytes);
+template <> __device__ __forceinline__ uint64_t make_sdesc_mn<bf16>(uint32_t saddr, uint32_t lbo_bytes) {
+  return make_sdesc(saddr, lbo_bytes, 1024);
+}
+template <> __device__ __forceinline__ uint64_t make_sdesc_mn<float>(uint32_t saddr, uint32_t lbo_bytes) {
+  return (make_sdesc(saddr, lbo_bytes, 512) & ~(7ull << 61)) | (1ull << 61);
+}
+
 __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
@@ -230,6 +247,32 @@ template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloa
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements (16 B fp32 / 8 B bf16, naturally aligned)
+template <typename T> __device__ __forceinline__ void load4(const T* p, float* f);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float* f) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float* f) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xFFFF0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xFFFF0000u);
+}
+// store 4 elements; returns the values as stored (after rounding to T) in f
+template <typename T> __device__ __forceinline__ void store4(T* p, float* f);
+template <> __device__ __forceinline__ void store4<float>(float* p, float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float* f) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&a);
+  pk.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = pk;
+  f[0] = __uint_as_float(pk.x << 16); f[1] = __uint_as_float(pk.x & 0xFFFF0000u);
+  f[2] = __uint_as_float(pk.y << 16); f[3] = __uint_as_float(pk.y & 0xFFFF0000u);
+}
 
 // ------------------------------------------------------------------------------------------------
 // tile row -> pixel.  Raster order, or 2x2-window-grouped order (rows 4q..4q+3 = one pooling

@@ -14,8 +14,7 @@
 //
 // Warp roles (320 threads): warps 0-7 A loaders then epilogue, warp 8 weight-copy producer,
 // warp 9 TMEM allocator + MMA issuer.  3-stage mbarrier ring; 2 CTAs / SM.
-#include "common.cuh"
-#include "../../include/cunet_b200.h"
+#include "loaders.cuh"
 #include "host_util.h"
 
 namespace cunet {
@@ -23,16 +22,13 @@ namespace cunet {
 constexpr int FWD_STAGES = 3;
 constexpr int FWD_STAGE_BYTES = 32768;  // 16 KB A tile + 16 KB B tile
 constexpr int FWD_THREADS = 320;
-constexpr int MAX_CIN = 512;
 
 struct FwdSmemTail {
   uint64_t full[FWD_STAGES];
   uint64_t empty[FWD_STAGES];
   uint64_t accum;
   uint32_t tmem_base;
-  int seg_start[CUNET_MAX_SEG + 1];
-  float scale[MAX_CIN];
-  float shift[MAX_CIN];
+  BnSmem bn;
 };
 
 template <typename T>
@@ -46,20 +42,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
   const int tile = blockIdx.x;
   const int grouped = p.pool;
 
-  int Cin = 0;
-  for (int s = 0; s < p.nseg; ++s) Cin += p.seg[s].C;
+  const int Cin = concat_cin(p.in);
   const int nkb = (Cin + E::KBE - 1) / E::KBE;  // K blocks per tap
   const int nsteps = p.taps * nkb;
   const uint32_t tmem_cols = p.CoutPad <= 32 ? 32 : (p.CoutPad <= 64 ? 64 : 128);
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
-    int acc = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      tail->seg_start[s] = acc;
-      acc += p.seg[s].C;
-    }
-    for (int s = p.nseg; s <= CUNET_MAX_SEG; ++s) tail->seg_start[s] = acc;
     for (int s = 0; s < FWD_STAGES; ++s) {
       mbar_init(&tail->full[s], 9);   // 8 loader warps + the producer's expect_tx arrive
       mbar_init(&tail->empty[s], 1);  // one tcgen05.commit
@@ -68,34 +57,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(&tail->tmem_base, tmem_cols);
-  // BN coefficients of this op's BatchNorm (nn.BatchNorm2d: biased batch variance in train mode)
-  for (int k = tid; k < nkb * E::KBE; k += FWD_THREADS) {
-    float sc = 0.f, sh = 0.f;
-    if (k < Cin) {
-      double mean, var;
-      if (p.bn_train) {
-        int s = 0, base = 0;
-        while (s + 1 < p.nseg && k >= base + p.seg[s].C) {
-          base += p.seg[s].C;
-          ++s;
-        }
-        const int c = k - base;
-        const double su = p.seg[s].stats[c], sq = p.seg[s].stats[p.seg[s].C + c];
-        mean = su * p.seg[s].inv_count;
-        var = sq * p.seg[s].inv_count - mean * mean;
-        if (var < 0.0) var = 0.0;
-      } else {
-        mean = p.rmean[k];
-        var = p.rvar[k];
-      }
-      const double istd = 1.0 / sqrt(var + (double)p.eps);
-      const double g = p.gamma[k];
-      sc = (float)(g * istd);
-      sh = (float)((double)p.beta[k] - mean * g * istd);
-    }
-    tail->scale[k] = sc;
-    tail->shift[k] = sh;
-  }
+  compute_bn_coefs(p.in, &tail->bn, nkb * E::KBE, tid, FWD_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -121,29 +83,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
       mask = 0;
       const int tap = it / nkb, kb = it - tap * nkb;
       const int ch = kb * E::KBE + c * E::EPC;
-      if (ch >= Cin) return;
-      int s = 0;
-      while (ch >= tail->seg_start[s + 1]) ++s;
-      const cunet_seg& sg = p.seg[s];
-      const int local = ch - tail->seg_start[s];
       int dy = 0, dx = 0;
       if (p.taps == 9) {
         dy = tap / 3 - 1;
         dx = tap - (tap / 3) * 3 - 1;
       }
-      const char* base = reinterpret_cast<const char*>(sg.ptr) + (size_t)local * E::ESZ;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (!((rvalid >> q) & 1)) continue;
-        const int hh = rh[q] + dy, ww = rw[q] + dx;
-        if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
-        long row;
-        if (sg.up)
-          row = ((long)rn[q] * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1);
-        else
-          row = ((long)rn[q] * p.H + hh) * p.W + ww;
-        dst[q] = ldg128(base + row * (long)sg.ld * E::ESZ);
-        mask |= 1u << q;
+        if (act_issue<T>(p.in, &tail->bn, p.H, p.W, ch, rn[q], rh[q], rw[q], dy, dx, dst[q])) mask |= 1u << q;
       }
     };
 
@@ -155,24 +103,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
       mbar_wait(&tail->empty[s], ph ^ 1);
       const int kb = it % nkb;
       const int ch = kb * E::KBE + c * E::EPC;
-      float sc[E::EPC], sh[E::EPC];
-#pragma unroll
-      for (int e = 0; e < E::EPC; ++e) {
-        sc[e] = tail->scale[ch + e];
-        sh[e] = tail->shift[ch + e];
-      }
       const uint32_t abase = smem_u32(smem + s * FWD_STAGE_BYTES);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = (tid >> 3) + 32 * q;
         uint4 o = make_uint4(0, 0, 0, 0);
-        if ((cmask >> q) & 1) {
-          float f[E::EPC];
-          Chunk<T>::unpack(cur[q], f);
-#pragma unroll
-          for (int e = 0; e < E::EPC; ++e) f[e] = fmaxf(fmaf(f[e], sc[e], sh[e]), 0.f);
-          o = Chunk<T>::pack_mma(f);
-        }
+        if ((cmask >> q) & 1) o = act_transform<T>(&tail->bn, ch, cur[q]);
         sts128(abase + tile_off(r, c), o);
       }
       fence_proxy_async();
@@ -320,15 +256,15 @@ using namespace cunet;
 
 extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   if (!p) return cunet_fail("conv_fwd: null params");
-  if (p->nseg < 1 || p->nseg > CUNET_MAX_SEG) return cunet_fail("conv_fwd: bad nseg");
+  if (p->in.nseg < 1 || p->in.nseg > CUNET_MAX_SEG) return cunet_fail("conv_fwd: bad nseg");
   if (p->taps != 1 && p->taps != 9) return cunet_fail("conv_fwd: taps must be 1 or 9");
   if (p->CoutPad % 16 || p->CoutPad < 16 || p->CoutPad > 128 || p->Cout > p->CoutPad)
     return cunet_fail("conv_fwd: CoutPad must be a multiple of 16 in [16,128]");
   int cin = 0;
-  for (int s = 0; s < p->nseg; ++s) {
-    if (p->seg[s].C % 32) return cunet_fail("conv_fwd: segment channels must be a multiple of 32");
-    if (p->bn_train && !p->seg[s].stats) return cunet_fail("conv_fwd: train-mode BN needs seg stats");
-    cin += p->seg[s].C;
+  for (int s = 0; s < p->in.nseg; ++s) {
+    if (p->in.seg[s].C % 32) return cunet_fail("conv_fwd: segment channels must be a multiple of 32");
+    if (p->in.bn_train && !p->in.seg[s].stats) return cunet_fail("conv_fwd: train-mode BN needs seg stats");
+    cin += p->in.seg[s].C;
   }
   if (cin > MAX_CIN) return cunet_fail("conv_fwd: too many input channels");
   if (p->out_stats && (256 % (p->CoutPad / 4) || p->Cout != p->CoutPad))

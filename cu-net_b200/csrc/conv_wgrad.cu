@@ -1,0 +1,234 @@
+// Backward-filter of the fused conv, sm_100a (autograd of nn.Conv2d w.r.t. its weight for one
+// cat -> BatchNorm -> ReLU -> conv call, models/cu_net.py:11-17).
+//
+//   dW[co][k][tap] += sum_px dY[px][co] * A[px + tap][k],     A = relu(bn(concat(x)))  (recomputed, never stored)
+//
+// GEMM view per CTA (one pixel range x one chunk of 128 concat channels x one tap):
+//   D[128 k][NPad co] += A^T[128 k][R px] * dY[R px][NPad co]          (contraction over pixels)
+// Both operands are gathered as pixel-row tiles ([px][128 B of channels], the same smem image the forward
+// kernel builds) and handed to tcgen05.mma as MN-major swizzled operands (bf16: SWIZZLE_128B, tf32:
+// SWIZZLE_128B_BASE32B), so no transpose is needed.
+// The fp32 accumulator stays in TMEM for the CTA's whole pixel range and is then reduced into the
+// reference-layout gradient with red.global.add.f32 (split-K over pixels across CTAs).
+#include "loaders.cuh"
+#include "host_util.h"
+
+namespace cunet {
+
+constexpr int WG_STAGES = 3;
+constexpr int WG_STAGE_BYTES = 32768;  // 16 KB activation sub-tiles + 16 KB gradient sub-tiles
+constexpr int WG_THREADS = 320;
+
+struct WgSmemTail {
+  uint64_t full[WG_STAGES];
+  uint64_t empty[WG_STAGES];
+  uint64_t accum;
+  uint32_t tmem_base;
+  BnSmem bn;
+  GradSmem gc;
+};
+
+template <typename T> struct WgGeom {
+  using E = Elem<T>;
+  static constexpr int R = 4 * E::MMA_K;    // pixel rows per stage: 64 (bf16) / 32 (fp32) -> 4 MMAs per stage
+  static constexpr int CPR = 128 / E::EPC;     // 16-byte chunks per pixel row of a 128-channel chunk
+  static constexpr int RPP = 256 / CPR;        // rows per loader pass
+  static constexpr int SUB_BYTES = R * 128;    // one sub-tile: R rows x 128 B
+};
+
+template <typename T>
+__global__ void __launch_bounds__(WG_THREADS, 2) conv_wgrad_kernel(const __grid_constant__ cunet_conv_wgrad_params p,
+                                                                    int nsplit, int npad) {
+  using E = Elem<T>;
+  using G = WgGeom<T>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + WG_STAGES * WG_STAGE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int chunk = blockIdx.y / p.taps, tap = blockIdx.y - chunk * p.taps;
+  const int Cin = concat_cin(p.in);
+  const long M = (long)p.N * p.H * p.W;
+  const int total_steps = (int)((M + G::R - 1) / G::R);
+  const int per = (total_steps + nsplit - 1) / nsplit;
+  const int st0 = split * per;
+  const int st1 = min(total_steps, st0 + per);
+  const int nsteps = max(0, st1 - st0);
+  int dy = 0, dx = 0;
+  if (p.taps == 9) {
+    dy = tap / 3 - 1;
+    dx = tap - (tap / 3) * 3 - 1;
+  }
+  const uint32_t tmem_cols = npad <= 32 ? 32 : (npad <= 64 ? 64 : 128);
+
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&tail->full[s], 8);
+      mbar_init(&tail->empty[s], 1);
+    }
+    mbar_init(&tail->accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&tail->tmem_base, tmem_cols);
+  compute_bn_coefs(p.in, &tail->bn, ((Cin + 127) / 128) * 128, tid, WG_THREADS);
+  compute_grad_coefs(p.dy, &tail->gc, tid, WG_THREADS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp < 8) {
+    // ============================================================== loaders
+    const int acc = tid % G::CPR, ar0 = tid / G::CPR;  // activation: fixed chunk column, 4 rows
+    const int ach = chunk * 128 + acc * E::EPC;
+    const int cprb = npad / E::EPC;                    // gradient chunks per pixel row
+    uint4 araw[4];
+    GradRaw<T> graw[4];
+
+    for (int it = 0; it < nsteps; ++it) {
+      const int s = it % WG_STAGES;
+      const uint32_t ph = (it / WG_STAGES) & 1;
+      const long m0 = (long)(st0 + it) * G::R;
+      uint32_t amask = 0, gmask = 0;
+      int gco[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long m = m0 + ar0 + G::RPP * q;
+        if (m < M) {
+          const int w = (int)(m % p.W);
+          const long t = m / p.W;
+          const int h = (int)(t % p.H), n = (int)(t / p.H);
+          if (act_issue<T>(p.in, &tail->bn, p.H, p.W, ach, n, h, w, dy, dx, araw[q])) amask |= 1u << q;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = tid + 256 * q;
+        gco[q] = 0;
+        if (idx < G::R * cprb) {
+          const int r = idx / cprb, cc = idx - r * cprb;
+          gco[q] = cc * E::EPC;
+          const long m = m0 + r;
+          if (m < M) {
+            const int w = (int)(m % p.W);
+            const long t = m / p.W;
+            const int h = (int)(t % p.H), n = (int)(t / p.H);
+            if (grad_issue<T>(p.dy, p.H, p.W, gco[q], n, h, w, graw[q])) gmask |= 1u << q;
+          }
+        }
+      }
+      mbar_wait(&tail->empty[s], ph ^ 1);
+      const uint32_t abase = smem_u32(smem + s * WG_STAGE_BYTES);
+      const uint32_t bbase = abase + 16384;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = ar0 + G::RPP * q;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if ((amask >> q) & 1) o = act_transform<T>(&tail->bn, ach, araw[q]);
+        sts128(abase + (acc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, acc & 7), o);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = tid + 256 * q;
+        if (idx < G::R * cprb) {
+          const int r = idx / cprb, cc = idx - r * cprb;
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if ((gmask >> q) & 1) o = grad_transform<T>(p.dy, &tail->gc, gco[q], graw[q]);
+          sts128(bbase + (cc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, cc & 7), o);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->full[s]);
+    }
+  } else if (warp == 9) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(E::FMT, 128, (uint32_t)npad, 1, 1);  // both operands MN-major
+      constexpr uint32_t KSTEP = E::MMA_K * 128;                             // bytes per MMA along K (pixel rows)
+      for (int it = 0; it < nsteps; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&tail->full[s], ph);
+        tc_fence_after();
+        const uint32_t a = smem_u32(smem + s * WG_STAGE_BYTES);
+        const uint32_t b = a + 16384;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          umma<T>(tmem, make_sdesc_mn<T>(a + kk * KSTEP, G::SUB_BYTES), make_sdesc_mn<T>(b + kk * KSTEP, G::SUB_BYTES),
+                  idesc, (uint32_t)((it | kk) != 0));
+        }
+        tc_commit(&tail->empty[s]);
+      }
+      tc_commit(&tail->accum);
+    }
+  }
+
+  // ================================================================== epilogue: TMEM -> red.global.add
+  if (warp < 8 && nsteps > 0) {
+    mbar_wait(&tail->accum, 0);
+    tc_fence_after();
+    const int lq = warp & 3, half = warp >> 2;
+    const int k = chunk * 128 + lq * 32 + lane;
+    const int nhalf = npad >> 1;
+    for (int j = 0; j < nhalf; j += 8) {
+      float v[8];
+      const int col = half * nhalf + j;
+      tmem_ld8(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col, v);
+      if (k < Cin) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int co = col + e;
+          if (co < p.Cout) atomicAdd(p.dw + ((long)co * Cin + k) * p.taps + tap, v[e]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace cunet
+using namespace cunet;
+
+extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) {
+  if (!p) return cunet_fail("conv_wgrad: null params");
+  if (p->in.nseg < 1 || p->in.nseg > CUNET_MAX_SEG) return cunet_fail("conv_wgrad: bad nseg");
+  if (p->taps != 1 && p->taps != 9) return cunet_fail("conv_wgrad: taps must be 1 or 9");
+  int cin = 0;
+  for (int s = 0; s < p->in.nseg; ++s) {
+    if (p->in.seg[s].C % 32) return cunet_fail("conv_wgrad: segment channels must be a multiple of 32");
+    if (p->in.bn_train && !p->in.seg[s].stats) return cunet_fail("conv_wgrad: train-mode BN needs seg stats");
+    cin += p->in.seg[s].C;
+  }
+  if (cin > MAX_CIN) return cunet_fail("conv_wgrad: too many input channels");
+  if (p->dy.C > 128 || p->Cout > 128) return cunet_fail("conv_wgrad: Cout > 128");
+  const long M = (long)p->N * p->H * p->W;
+  if (M <= 0) return 0;
+  const int kbe = p->dtype == CUNET_BF16 ? 64 : 32;
+  const int R = p->dtype == CUNET_BF16 ? 64 : 32;
+  const int npad = ((p->dy.C + kbe - 1) / kbe) * kbe;  // whole MN groups of the gradient operand
+  const int ny = ((cin + 127) / 128) * p->taps;
+  const int total_steps = (int)((M + R - 1) / R);
+  int nsplit = p->nsplit > 0 ? p->nsplit : (296 + ny - 1) / ny;
+  if (nsplit > total_steps) nsplit = total_steps;
+  if (nsplit < 1) nsplit = 1;
+  dim3 grid((unsigned)nsplit, (unsigned)ny);
+  const size_t smem = WG_STAGES * WG_STAGE_BYTES + sizeof(WgSmemTail) + 1024;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (p->dtype == CUNET_BF16) {
+    e = cudaFuncSetAttribute(conv_wgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cunet_fail_cuda("conv_wgrad attr", e);
+    conv_wgrad_kernel<bf16><<<grid, WG_THREADS, smem, st>>>(*p, nsplit, npad);
+  } else {
+    e = cudaFuncSetAttribute(conv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cunet_fail_cuda("conv_wgrad attr", e);
+    conv_wgrad_kernel<float><<<grid, WG_THREADS, smem, st>>>(*p, nsplit, npad);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_wgrad launch", e);
+  return 0;
+}

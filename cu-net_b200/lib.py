@@ -23,15 +23,43 @@ class Seg(C.Structure):
                 ("C", C.c_int), ("ld", C.c_int), ("up", C.c_int), ("reserved", C.c_int)]
 
 
-class ConvFwdParams(C.Structure):
-    _fields_ = [("seg", Seg * MAX_SEG), ("nseg", C.c_int),
-                ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
+class Concat(C.Structure):
+    _fields_ = [("seg", Seg * MAX_SEG), ("nseg", C.c_int), ("bn_train", C.c_int),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("rmean", C.c_void_p), ("rvar", C.c_void_p),
-                ("bn_train", C.c_int), ("eps", C.c_float),
+                ("eps", C.c_float), ("reserved", C.c_int)]
+
+
+class ConvFwdParams(C.Structure):
+    _fields_ = [("inp", Concat),
+                ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
                 ("wpack", C.c_void_p), ("Cout", C.c_int), ("CoutPad", C.c_int),
                 ("out", C.c_void_p), ("out_ld", C.c_int), ("out_fp32", C.c_int),
-                ("out_stats", C.c_void_p), ("pool", C.c_int), ("pool_idx", C.c_void_p),
+                ("out_stats", C.c_void_p), ("pool_idx", C.c_void_p), ("pool", C.c_int),
                 ("dtype", C.c_int)]
+
+
+class GradSrc(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("t", C.c_void_p), ("stats", C.c_void_p), ("gstats", C.c_void_p),
+                ("pool_idx", C.c_void_p), ("inv_count", C.c_double),
+                ("C", C.c_int), ("ld", C.c_int), ("mode", C.c_int), ("pooled", C.c_int),
+                ("eps", C.c_float), ("reserved", C.c_int)]
+
+
+class GAcc(C.Structure):
+    _fields_ = [("G", C.c_void_p), ("gstats", C.c_void_p), ("ld", C.c_int), ("accumulate", C.c_int)]
+
+
+class ConvDgradParams(C.Structure):
+    _fields_ = [("inp", Concat), ("gacc", GAcc * MAX_SEG), ("dy", GradSrc),
+                ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
+                ("wpack_dgrad", C.c_void_p), ("Cout", C.c_int), ("CoutPad", C.c_int),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dtype", C.c_int), ("reserved", C.c_int)]
+
+
+class ConvWgradParams(C.Structure):
+    _fields_ = [("inp", Concat), ("dy", GradSrc),
+                ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
+                ("Cout", C.c_int), ("dw", C.c_void_p), ("nsplit", C.c_int), ("dtype", C.c_int)]
 
 
 class PackDesc(C.Structure):
@@ -64,7 +92,7 @@ def load():
 # every symbol include/cunet_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "cunet_last_error", "cunet_abi_version",
-    "cunet_conv_fwd", "cunet_pack_weights", "cunet_pack_fwd_bytes", "cunet_pack_dgrad_bytes",
+    "cunet_conv_fwd", "cunet_conv_dgrad", "cunet_conv_wgrad", "cunet_pack_weights", "cunet_pack_fwd_bytes", "cunet_pack_dgrad_bytes",
 ]
 
 
@@ -87,6 +115,14 @@ def dptr(t):
 
 def conv_fwd(params):
     check(load().cunet_conv_fwd(C.byref(params), stream_ptr()), "cunet_conv_fwd")
+
+
+def conv_dgrad(params):
+    check(load().cunet_conv_dgrad(C.byref(params), stream_ptr()), "cunet_conv_dgrad")
+
+
+def conv_wgrad(params):
+    check(load().cunet_conv_wgrad(C.byref(params), stream_ptr()), "cunet_conv_wgrad")
 
 
 def pack_weights(descs_dev_ptr, ndesc, dtype):

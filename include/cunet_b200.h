@@ -38,34 +38,103 @@ typedef struct {
   int reserved;
 } cunet_seg;
 
+/* A virtual concat + the BatchNorm(+ReLU) that precedes a conv: the "A operand" of every fused conv
+ * (torch.cat -> norm -> relu of _bn_function_factory, models/cu_net.py:11-17). */
+typedef struct {
+  cunet_seg seg[CUNET_MAX_SEG];
+  int nseg;
+  int bn_train;       /* 1: batch statistics from seg[].stats; 0: running statistics */
+  const float* gamma; /* [Cin] BN weight, concat order                 */
+  const float* beta;  /* [Cin] BN bias                                 */
+  const float* rmean; /* [Cin] running mean  (eval mode)               */
+  const float* rvar;  /* [Cin] running var   (eval mode)               */
+  float eps;
+  int reserved;
+} cunet_concat;
+
 /* Fused  cat -> BatchNorm -> ReLU -> conv(1x1 | 3x3 pad 1)  [-> 2x2 maxpool]  forward.
  * Replaces _bn_function_factory + nn.Conv2d (models/cu_net.py:11-17, 24, 43, 47-48, 197) and the
  * nn.MaxPool2d that follows a down-block's adapters_ahead (models/cu_net.py:249, 260).
  * Epilogue also accumulates the per-channel sum / sum-of-squares of the tensor it writes, which is the
  * batch statistic every consumer BatchNorm of that tensor needs (nn.BatchNorm2d train mode). */
 typedef struct {
-  cunet_seg seg[CUNET_MAX_SEG];
-  int nseg;
+  cunet_concat in;
   int N, H, W;        /* output resolution (before the optional pool) */
   int taps;           /* 1 (1x1) or 9 (3x3, pad 1)                     */
-  const float* gamma; /* [Cin] BN weight, concat order                 */
-  const float* beta;  /* [Cin] BN bias                                 */
-  const float* rmean; /* [Cin] running mean  (eval mode)               */
-  const float* rvar;  /* [Cin] running var   (eval mode)               */
-  int bn_train;       /* 1: batch statistics from seg[].stats; 0: running statistics */
-  float eps;
   const void* wpack;  /* packed weights from cunet_pack_weights (fwd image) */
   int Cout, CoutPad;  /* CoutPad: multiple of 16, <= 128              */
   void* out;          /* [rows][out_ld]                                */
   int out_ld;
   int out_fp32;       /* 1: store fp32 regardless of dtype (heatmap heads) */
   double* out_stats;  /* [2*Cout] accumulated (+=) or NULL             */
-  int pool;           /* 1: write maxpool2x2(out) [N*H/2*W/2][out_ld] + pool_idx */
   uint8_t* pool_idx;  /* [N*H/2*W/2][Cout] argmax position (dy*2+dx) or NULL */
+  int pool;           /* 1: write maxpool2x2(out) [N*H/2*W/2][out_ld] + pool_idx */
   int dtype;          /* CUNET_F32 (tf32 MMA) or CUNET_BF16           */
 } cunet_conv_fwd_params;
 
 int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream);
+
+/* The gradient w.r.t. a conv's OUTPUT tensor T, as the backward kernels consume it.
+ * Every tensor of the network is consumed only through BatchNorm'd convs, so its gradient is
+ *   dT = istd * (G - mean(G) - xhat * mean(G*xhat)),   G = sum over consumers of gamma_j * dz_j
+ * (autograd of nn.BatchNorm2d train mode, summed over the consumers that share T's batch statistics).
+ * The dgrad kernels of the consumers accumulate G and (sum G, sum G*T); the producer's backward kernels
+ * evaluate dT on the fly as  p*G + q*T + r  per channel.  mode 0: dT = g (plain, e.g. dLoss/dhead).
+ * pooled = 1: T is the 2x2-maxpooled conv output (g, t, pool_idx at half resolution); the gradient is
+ * routed to the argmax position (autograd of nn.MaxPool2d, models/cu_net.py:249,260). */
+typedef struct {
+  const void* g;
+  const void* t;
+  const double* stats;     /* [2*C] sum, sumsq of T (forward)         */
+  const double* gstats;    /* [2*C] sum G, sum G*T                     */
+  const uint8_t* pool_idx; /* [rows][C] or NULL                        */
+  double inv_count;        /* 1 / rows of T                            */
+  int C, ld;
+  int mode;                /* 0 plain, 1 batch-norm backward form      */
+  int pooled;
+  float eps;
+  int reserved;
+} cunet_grad_src;
+
+/* Per-source accumulator written by a consumer's dgrad epilogue. */
+typedef struct {
+  void* G;        /* [rows][ld] dtype; NULL: this source needs no gradient  */
+  double* gstats; /* non-NULL: this is the last consumer -> accumulate (sum G, sum G*T) of the final G */
+  int ld;
+  int accumulate; /* 0: first consumer in backward order (write), 1: read-modify-write */
+} cunet_gacc;
+
+/* Backward-data of the fused conv (autograd of nn.Conv2d + ReLU + BatchNorm2d + cat/upsample split,
+ * SURVEY.md section 8 A15): dA = dY * W, then per source: dz = dA * [bn(x) > 0],
+ * dgamma += sum dz*xhat, dbeta += sum dz, G_src += gamma*dz (summing the 4 children of an upsampled src). */
+typedef struct {
+  cunet_concat in;         /* the conv's input side, exactly as in the forward call */
+  cunet_gacc gacc[CUNET_MAX_SEG];
+  cunet_grad_src dy;       /* gradient of the conv's output */
+  int N, H, W, taps;
+  const void* wpack_dgrad; /* dgrad image from cunet_pack_weights */
+  int Cout, CoutPad;
+  float* dgamma;           /* [Cin] fp32, accumulated with atomics (caller zeroes once per step) */
+  float* dbeta;            /* [Cin] */
+  int dtype;
+  int reserved;
+} cunet_conv_dgrad_params;
+
+int cunet_conv_dgrad(const cunet_conv_dgrad_params* p, void* stream);
+
+/* Backward-filter of the fused conv: dW[co][k][tap] += sum_px dY[px][co] * relu(bn(x))[px+tap][k]
+ * (autograd of nn.Conv2d w.r.t. weight), accumulated into the reference-layout fp32 gradient. */
+typedef struct {
+  cunet_concat in;
+  cunet_grad_src dy;
+  int N, H, W, taps;
+  int Cout;
+  float* dw;               /* [Cout][Cin][taps] fp32, atomically accumulated */
+  int nsplit;              /* CTAs along the pixel dimension (0: library default) */
+  int dtype;
+} cunet_conv_wgrad_params;
+
+int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream);
 
 /* Weight packing: reference-layout fp32 master weights -> tensor-core operand images.
  * One descriptor per conv; all descriptors processed by one launch.

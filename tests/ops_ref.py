@@ -59,3 +59,71 @@ def conv_fwd_ref(srcs, ups, n, h, w, scale, shift, weight, pool=False):
         idx = ((hh % 2) * 2 + (ww % 2)).to(torch.uint8)
         idx = nchw_to_rows(idx)
     return nchw_to_rows(y), idx
+
+
+def grad_coeffs(stats, gstats, count, eps=1e-5):
+    """p, q, r of dT = p*G + q*T + r (batch-norm backward form, see include/cunet_b200.h)."""
+    c = stats.numel() // 2
+    mean = stats[:c] / count
+    var = (stats[c:] / count - mean * mean).clamp_min(0)
+    istd = 1.0 / torch.sqrt(var + eps)
+    s1 = gstats[:c]
+    s2 = istd * (gstats[c:] - mean * s1)
+    q = -istd * istd * s2 / count
+    p = istd
+    r = -istd * s1 / count - q * mean
+    return p.float(), q.float(), r.float()
+
+
+def grad_src_eval(g, t, coeffs, pool_idx, n, h, w):
+    """Full-resolution gradient rows dT [n*h*w][C] of a (possibly pooled) conv output.
+
+    g, t: rows at h,w (or h/2,w/2 when pool_idx is given); coeffs: (p,q,r) or None (plain)."""
+    d = g.float()
+    if coeffs is not None:
+        p, q, r = coeffs
+        d = p * d + q * t.float() + r
+    if pool_idx is None:
+        return d
+    c = d.shape[1]
+    dn = rows_to_nchw(d, n, h // 2, w // 2)
+    idx = pool_idx.reshape(n, h // 2, w // 2, c).permute(0, 3, 1, 2).long()
+    full = torch.zeros(n, c, h, w, device=d.device)
+    for pos in range(4):
+        dy, dx = pos // 2, pos % 2
+        full[:, :, dy::2, dx::2] = torch.where(idx == pos, dn, torch.zeros_like(dn))
+    return nchw_to_rows(full)
+
+
+def conv_bwd_ref(srcs, ups, n, h, w, scale, shift, mean, istd, gamma, weight, dy_rows):
+    """Reference backward of cat->BN(train, stats held fixed)->ReLU->conv for the kernels' contract.
+
+    Returns (G_contrib per source [at source resolution], dgamma, dbeta, dW).  G = gamma * dz."""
+    xs = []
+    for s, up in zip(srcs, ups):
+        if up:
+            x = F.interpolate(rows_to_nchw(s, n, h // 2, w // 2), scale_factor=2, mode="nearest")
+        else:
+            x = rows_to_nchw(s, n, h, w)
+        xs.append(x)
+    x = torch.cat(xs, 1)
+    z = x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    a = F.relu(z).detach().requires_grad_(True)
+    wt = weight.detach().clone().requires_grad_(True)
+    y = F.conv2d(a, wt, padding=weight.shape[-1] // 2)
+    dy = rows_to_nchw(dy_rows, n, h, w)[:, :weight.shape[0]]
+    da, dw = torch.autograd.grad(y, [a, wt], dy)
+    dz = da * (z > 0).float()
+    xhat = (x - mean.view(1, -1, 1, 1).float()) * istd.view(1, -1, 1, 1).float()
+    dbeta = dz.sum((0, 2, 3))
+    dgamma = (dz * xhat).sum((0, 2, 3))
+    gc = dz * gamma.view(1, -1, 1, 1)
+    outs, c0 = [], 0
+    for s, up in zip(srcs, ups):
+        c = s.shape[1]
+        part = gc[:, c0:c0 + c]
+        if up:
+            part = F.avg_pool2d(part, 2, 2) * 4
+        outs.append(nchw_to_rows(part))
+        c0 += c
+    return outs, dgamma, dbeta, dw

@@ -1,0 +1,158 @@
+"""GPU parity of the backward kernels (cunet_conv_dgrad, cunet_conv_wgrad) through the C ABI."""
+import pytest
+import torch
+
+from tests import ops_ref
+from tests.test_gpu_conv_fwd import fill_concat, _relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(lib, dtype, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad=None, seed=0):
+    """dy_mode: 'plain' | 'bn' | 'pool' (bn form routed through a 2x2 max-pool argmax)."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    td = torch.bfloat16 if dtype == lib.BF16 else torch.float32
+    cout_pad = cout_pad or cout
+    srcs, stats, counts = [], [], []
+    for c, up in zip(seg_c, ups):
+        hh, ww = (h // 2, w // 2) if up else (h, w)
+        x = (torch.randn(n * hh * ww, c, generator=g) * 1.3 + 0.4).to(dev).to(td)
+        srcs.append(x)
+        stats.append(ops_ref.tensor_stats(x))
+        counts.append(n * hh * ww)
+    cin = sum(seg_c)
+    gamma = (torch.rand(cin, generator=g) + 0.1).to(dev)
+    beta = (torch.randn(cin, generator=g) * 0.2).to(dev)
+    k = 3 if taps == 9 else 1
+    weight = ((torch.rand(cout, cin, k, k, generator=g) * 2 - 1) / (cin * k * k) ** 0.5).to(dev)
+    # gradient source of the conv output
+    ho, wo = (h // 2, w // 2) if dy_mode == "pool" else (h, w)
+    rows = n * ho * wo
+    gten = (torch.randn(rows, cout_pad, generator=g) * 0.1).to(dev).to(td)
+    if cout_pad > cout:
+        gten[:, cout:] = 0
+    tten = (torch.randn(rows, cout_pad, generator=g) * 1.1 + 0.3).to(dev).to(td)
+    tstats = ops_ref.tensor_stats(tten)
+    gstats = torch.cat([gten.double().sum(0), (gten.double() * tten.double()).sum(0)])
+    pidx = None
+    if dy_mode == "pool":
+        pidx = torch.randint(0, 4, (rows, cout_pad), generator=g).to(torch.uint8).to(dev)
+    return dict(srcs=srcs, stats=stats, counts=counts, gamma=gamma, beta=beta, weight=weight, g=gten, t=tten,
+                tstats=tstats, gstats=gstats, pidx=pidx, rows=rows, cin=cin, cout_pad=cout_pad, td=td, dev=dev)
+
+
+def fill_grad_src(gs, cs, dy_mode):
+    gs.g, gs.t = cs["g"].data_ptr(), cs["t"].data_ptr()
+    gs.stats, gs.gstats = cs["tstats"].data_ptr(), cs["gstats"].data_ptr()
+    gs.pool_idx = cs["pidx"].data_ptr() if cs["pidx"] is not None else None
+    gs.inv_count = 1.0 / cs["rows"]
+    gs.C, gs.ld = cs["cout_pad"], cs["cout_pad"]
+    gs.mode = 0 if dy_mode == "plain" else 1
+    gs.pooled = int(dy_mode == "pool")
+    gs.eps = 1e-5
+
+
+def reference(cs, n, h, w, ups, dy_mode):
+    scale, shift, mean, var = ops_ref.bn_coeffs(cs["stats"], cs["counts"], cs["gamma"], cs["beta"])
+    istd = 1.0 / torch.sqrt(var + 1e-5)
+    coeffs = None if dy_mode == "plain" else ops_ref.grad_coeffs(cs["tstats"], cs["gstats"], cs["rows"])
+    dy = ops_ref.grad_src_eval(cs["g"], cs["t"], coeffs, cs["pidx"], n, h, w)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return ops_ref.conv_bwd_ref([s.float() for s in cs["srcs"]], ups, n, h, w, scale, shift, mean, istd,
+                                cs["gamma"], cs["weight"], dy)
+
+
+CASES = [
+    # name, n,h,w, seg_c, ups, cout, taps, dy_mode, cout_pad
+    ("1x1_128_plain", 2, 16, 16, [128], [0], 128, 1, "plain", None),
+    ("1x1_192_bn", 2, 16, 16, [128, 32, 32], [0, 0, 0], 128, 1, "bn", None),
+    ("1x1_192_pool", 2, 16, 16, [128, 32, 32], [0, 0, 0], 128, 1, "pool", None),
+    ("1x1_320_up_bn", 2, 16, 16, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, "bn", None),
+    ("3x3_bn", 2, 16, 16, [128], [0], 32, 9, "bn", None),
+    ("head68_plain", 2, 16, 16, [128], [0], 68, 1, "plain", 80),
+    ("1x1_tail_bn", 3, 4, 4, [128, 32], [0, 0], 128, 1, "bn", None),
+    ("1x1_up_tail", 3, 4, 4, [128, 128, 32], [1, 0, 0], 128, 1, "bn", None),
+    ("3x3_tail", 3, 4, 4, [128], [0], 32, 9, "bn", None),
+    ("1x1_big_bn", 4, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, "bn", None),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_conv_wgrad(case, dtype_name):
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.F32 if dtype_name == "f32" else lib.BF16
+    name, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad = case
+    cs = make_case(lib, dtype, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad)
+    dw = torch.zeros(cout, cs["cin"], taps, device=cs["dev"])
+    p = lib.ConvWgradParams()
+    fill_concat(p.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"],
+                cs["gamma"], True)
+    fill_grad_src(p.dy, cs, dy_mode)
+    p.N, p.H, p.W, p.taps, p.Cout = n, h, w, taps, cout
+    p.dw, p.nsplit, p.dtype = dw.data_ptr(), 0, dtype
+    lib.conv_wgrad(p)
+    torch.cuda.synchronize()
+    _, _, _, dw_ref = reference(cs, n, h, w, ups, dy_mode)
+    err = _relerr(dw.reshape(dw_ref.shape[0], dw_ref.shape[1], -1), dw_ref.reshape(dw_ref.shape[0], dw_ref.shape[1], -1))
+    tol = 3e-3 if dtype == lib.F32 else 2e-2
+    assert err < tol, "%s %s dW rel err %g" % (name, dtype_name, err)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_conv_dgrad(case, dtype_name):
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.F32 if dtype_name == "f32" else lib.BF16
+    name, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad = case
+    cs = make_case(lib, dtype, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad)
+    dev, td = cs["dev"], cs["td"]
+    cin = cs["cin"]
+    # pack dgrad image
+    nbytes = lib.pack_dgrad_bytes(cin, taps, cs["cout_pad"], dtype)
+    wpack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    desc = lib.PackDesc(cs["weight"].data_ptr(), None, wpack.data_ptr(), cout, cin, taps, cs["cout_pad"])
+    desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).to(dev)
+    lib.pack_weights(desc_dev.data_ptr(), 1, dtype)
+
+    p = lib.ConvDgradParams()
+    fill_concat(p.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"],
+                cs["gamma"], True)
+    fill_grad_src(p.dy, cs, dy_mode)
+    gen = torch.Generator(device="cpu").manual_seed(99)
+    Gs, G0, gst = [], [], []
+    for i, x in enumerate(cs["srcs"]):
+        accumulate = i % 2          # alternate write / read-modify-write
+        g0 = (torch.randn(x.shape, generator=gen) * 0.05).to(dev).to(td) if accumulate else \
+            torch.full(x.shape, float("nan"), device=dev, dtype=td)
+        G0.append(g0.clone())
+        Gs.append(g0)
+        st = torch.zeros(2 * x.shape[1], dtype=torch.float64, device=dev)
+        gst.append(st)
+        p.gacc[i].G = g0.data_ptr()
+        p.gacc[i].gstats = st.data_ptr()
+        p.gacc[i].ld = x.shape[1]
+        p.gacc[i].accumulate = accumulate
+    dgamma = torch.zeros(cin, device=dev)
+    dbeta = torch.zeros(cin, device=dev)
+    p.N, p.H, p.W, p.taps = n, h, w, taps
+    p.wpack_dgrad, p.Cout, p.CoutPad = wpack.data_ptr(), cout, cs["cout_pad"]
+    p.dgamma, p.dbeta, p.dtype = dgamma.data_ptr(), dbeta.data_ptr(), dtype
+    lib.conv_dgrad(p)
+    torch.cuda.synchronize()
+
+    outs, dg_ref, db_ref, _ = reference(cs, n, h, w, ups, dy_mode)
+    tol = 3e-3 if dtype == lib.F32 else 2.5e-2
+    for i, (G, ref) in enumerate(zip(Gs, outs)):
+        exp = ref + (G0[i].float() if i % 2 else 0)
+        assert torch.isfinite(G.float()).all(), "segment %d has unwritten rows" % i
+        err = _relerr(G.float(), exp)
+        assert err < tol, "%s %s G[%d] rel err %g" % (name, dtype_name, i, err)
+        st_ref = torch.cat([G.double().sum(0), (G.double() * cs["srcs"][i].double()).sum(0)])
+        assert _relerr(gst[i], st_ref) < 1e-3, "gstats %d" % i
+    assert _relerr(dbeta, db_ref) < tol, "dbeta %g" % _relerr(dbeta, db_ref)
+    assert _relerr(dgamma, dg_ref) < tol, "dgamma %g" % _relerr(dgamma, dg_ref)

@@ -13,6 +13,19 @@ def _mk(lib, dtype):
     return torch.bfloat16 if dtype == lib.BF16 else torch.float32
 
 
+def fill_concat(cc, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train):
+    cc.nseg = len(srcs)
+    for i, (x, st, cnt, up) in enumerate(zip(srcs, stats, counts, ups)):
+        cc.seg[i].ptr = x.data_ptr()
+        cc.seg[i].stats = st.data_ptr()
+        cc.seg[i].inv_count = 1.0 / cnt
+        cc.seg[i].C = x.shape[1]
+        cc.seg[i].ld = x.shape[1]
+        cc.seg[i].up = int(up)
+    cc.gamma, cc.beta, cc.rmean, cc.rvar = gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr()
+    cc.bn_train, cc.eps = int(train), 1e-5
+
+
 def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=True, out_fp32=False,
                  cout_pad=None, seed=0):
     dev = torch.device("cuda")
@@ -48,17 +61,8 @@ def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=
     pidx = torch.zeros(rows_out, cout, dtype=torch.uint8, device=dev) if pool else None
 
     p = lib.ConvFwdParams()
-    p.nseg = len(srcs)
-    for i, (x, st, cnt, up) in enumerate(zip(srcs, stats, counts, ups)):
-        p.seg[i].ptr = x.data_ptr()
-        p.seg[i].stats = st.data_ptr()
-        p.seg[i].inv_count = 1.0 / cnt
-        p.seg[i].C = x.shape[1]
-        p.seg[i].ld = x.shape[1]
-        p.seg[i].up = int(up)
+    fill_concat(p.inp, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train)
     p.N, p.H, p.W, p.taps = n, h, w, taps
-    p.gamma, p.beta, p.rmean, p.rvar = gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr()
-    p.bn_train, p.eps = int(train), 1e-5
     p.wpack, p.Cout, p.CoutPad = wpack.data_ptr(), cout, cout_pad
     p.out, p.out_ld, p.out_fp32 = out.data_ptr(), out_ld, int(out_fp32)
     p.out_stats = out_stats.data_ptr() if out_stats is not None else None
