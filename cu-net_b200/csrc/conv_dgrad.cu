@@ -12,14 +12,13 @@
 // Epilogue (per source segment of the concat):  x = source value, z = scale*x + shift,
 //   dz = dA * [z > 0];  dbeta += sum dz;  dgamma += sum dz * xhat;  G_src (+)= gamma * dz
 //   (for an upsampled source the four children are summed first), and for the last consumer of a
-//   source the per-channel (sum G, sum G*T) that the producer's backward needs.
+//   source the per-channel (sum G, sum G*xhat) that the producer's backward needs.
 #include "loaders.cuh"
 #include "host_util.h"
 
 namespace cunet {
 
 constexpr int DG_STAGES = 3;
-constexpr int DG_STAGE_BYTES = 32768;
 constexpr int DG_THREADS = 320;
 
 struct DgSmemTail {
@@ -32,11 +31,12 @@ struct DgSmemTail {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(DG_THREADS, 2) conv_dgrad_kernel(const __grid_constant__ cunet_conv_dgrad_params p) {
+__global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad_kernel(const __grid_constant__ cunet_conv_dgrad_params p) {
   using E = Elem<T>;
+  using SG = StageGeom<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  DgSmemTail* tail = reinterpret_cast<DgSmemTail*>(smem + DG_STAGES * DG_STAGE_BYTES);
+  DgSmemTail* tail = reinterpret_cast<DgSmemTail*>(smem + DG_STAGES * SG::BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, chunk = blockIdx.y;
@@ -106,13 +106,14 @@ __global__ void __launch_bounds__(DG_THREADS, 2) conv_dgrad_kernel(const __grid_
       const uint32_t ph = (it / DG_STAGES) & 1;
       if (it + 1 < nsteps) issue(it + 1, nxt, nmask, nco);
       mbar_wait(&tail->empty[s], ph ^ 1);
-      const uint32_t abase = smem_u32(smem + s * DG_STAGE_BYTES);
+      const uint32_t abase = smem_u32(smem + s * SG::BYTES);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = (tid >> 3) + 32 * q;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if ((cmask >> q) & 1) o = grad_transform<T>(p.dy, &tail->gc, cco, cur[q]);
+        uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+        if ((cmask >> q) & 1) o = grad_transform<T>(p.dy, &tail->gc, cco, cur[q], lo);
         sts128(abase + tile_off(r, c), o);
+        if (SG::SPLIT) sts128(abase + SG::A_LO + tile_off(r, c), lo);
       }
       fence_proxy_async();
       __syncwarp();
@@ -124,14 +125,14 @@ __global__ void __launch_bounds__(DG_THREADS, 2) conv_dgrad_kernel(const __grid_
     }
   } else if (warp == 8) {
     if (lane == 0) {
-      const uint32_t bbytes = 128u * 128u;
+      const uint32_t bbytes = 128u * 128u * (SG::SPLIT ? 2u : 1u);
       const char* w = reinterpret_cast<const char*>(p.wpack_dgrad) + (size_t)chunk * nsteps * bbytes;
       for (int it = 0; it < nsteps; ++it) {
         const int s = it % DG_STAGES;
         const uint32_t ph = (it / DG_STAGES) & 1;
         mbar_wait(&tail->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&tail->full[s], bbytes);
-        bulk_g2s(smem + s * DG_STAGE_BYTES + 16384, w + (size_t)it * bbytes, bbytes, &tail->full[s]);
+        bulk_g2s(smem + s * SG::BYTES + SG::B_OFF, w + (size_t)it * bbytes, bbytes, &tail->full[s]);
       }
     }
   } else {
@@ -142,12 +143,17 @@ __global__ void __launch_bounds__(DG_THREADS, 2) conv_dgrad_kernel(const __grid_
         const uint32_t ph = (it / DG_STAGES) & 1;
         mbar_wait(&tail->full[s], ph);
         tc_fence_after();
-        const uint32_t a = smem_u32(smem + s * DG_STAGE_BYTES);
-        const uint32_t b = a + 16384;
+        const uint32_t a = smem_u32(smem + s * SG::BYTES);
+        const uint32_t b = a + SG::B_OFF;
+        const uint32_t alo = a + SG::A_LO, blo = b + 16384u;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           umma<T>(tmem, make_sdesc(a + kk * 32, 16, 1024), make_sdesc(b + kk * 32, 16, 1024), idesc,
                   (uint32_t)((it | kk) != 0));
+          if (SG::SPLIT) {
+            umma<T>(tmem, make_sdesc(alo + kk * 32, 16, 1024), make_sdesc(b + kk * 32, 16, 1024), idesc, 1u);
+            umma<T>(tmem, make_sdesc(a + kk * 32, 16, 1024), make_sdesc(blo + kk * 32, 16, 1024), idesc, 1u);
+          }
         }
         tc_commit(&tail->empty[s]);
       }
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(DG_THREADS, 2) conv_dgrad_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             a_g[e] += gv[e];
-            a_gt[e] += gv[e] * x[e];
+            a_gt[e] += gv[e] * (x[e] - mu[e]) * is[e];
           }
         }
       }
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(DG_THREADS, 2) conv_dgrad_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             a_g[e] += gv[e];
-            a_gt[e] += gv[e] * x[e];
+            a_gt[e] += gv[e] * (x[e] - mu[e]) * is[e];
           }
         }
       }
@@ -318,7 +324,7 @@ extern "C" int cunet_conv_dgrad(const cunet_conv_dgrad_params* p, void* stream) 
   if (!p) return cunet_fail("conv_dgrad: null params");
   if (p->in.nseg < 1 || p->in.nseg > CUNET_MAX_SEG) return cunet_fail("conv_dgrad: bad nseg");
   if (p->taps != 1 && p->taps != 9) return cunet_fail("conv_dgrad: taps must be 1 or 9");
-  if (!p->in.bn_train) return cunet_fail("conv_dgrad: backward requires train-mode BN statistics");
+  if (p->in.bn_train != 1) return cunet_fail("conv_dgrad: backward requires train-mode BN statistics");
   int cin = 0, up = 0;
   for (int s = 0; s < p->in.nseg; ++s) {
     if (p->in.seg[s].C % 32) return cunet_fail("conv_dgrad: segment channels must be a multiple of 32");
@@ -332,7 +338,8 @@ extern "C" int cunet_conv_dgrad(const cunet_conv_dgrad_params* p, void* stream) 
   if (M <= 0) return 0;
   const long tiles = up ? (M / 4 + 31) / 32 : (M + 127) / 128;
   dim3 grid((unsigned)tiles, (unsigned)((cin + 127) / 128));
-  const size_t smem = DG_STAGES * DG_STAGE_BYTES + sizeof(DgSmemTail) + 1024;
+  const size_t smem = DG_STAGES * (p->dtype == CUNET_BF16 ? StageGeom<bf16>::BYTES : StageGeom<float>::BYTES) +
+                      sizeof(DgSmemTail) + 1024;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (p->dtype == CUNET_BF16) {

@@ -20,7 +20,6 @@
 namespace cunet {
 
 constexpr int FWD_STAGES = 3;
-constexpr int FWD_STAGE_BYTES = 32768;  // 16 KB A tile + 16 KB B tile
 constexpr int FWD_THREADS = 320;
 
 struct FwdSmemTail {
@@ -32,11 +31,12 @@ struct FwdSmemTail {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_constant__ cunet_conv_fwd_params p) {
+__global__ void __launch_bounds__(FWD_THREADS, StageGeom<T>::MIN_CTAS) conv_fwd_kernel(const __grid_constant__ cunet_conv_fwd_params p) {
   using E = Elem<T>;
+  using SG = StageGeom<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  FwdSmemTail* tail = reinterpret_cast<FwdSmemTail*>(smem + FWD_STAGES * FWD_STAGE_BYTES);
+  FwdSmemTail* tail = reinterpret_cast<FwdSmemTail*>(smem + FWD_STAGES * SG::BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
@@ -103,13 +103,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
       mbar_wait(&tail->empty[s], ph ^ 1);
       const int kb = it % nkb;
       const int ch = kb * E::KBE + c * E::EPC;
-      const uint32_t abase = smem_u32(smem + s * FWD_STAGE_BYTES);
+      const uint32_t abase = smem_u32(smem + s * SG::BYTES);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = (tid >> 3) + 32 * q;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if ((cmask >> q) & 1) o = act_transform<T>(&tail->bn, ch, cur[q]);
+        uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+        if ((cmask >> q) & 1) o = act_transform<T>(&tail->bn, ch, cur[q], lo);
         sts128(abase + tile_off(r, c), o);
+        if (SG::SPLIT) sts128(abase + SG::A_LO + tile_off(r, c), lo);
       }
       fence_proxy_async();
       __syncwarp();
@@ -121,14 +122,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
   } else if (warp == 8) {
     // ============================================================== weight producer (TMA bulk)
     if (lane == 0) {
-      const uint32_t bbytes = (uint32_t)p.CoutPad * 128u;
+      const uint32_t bbytes = (uint32_t)p.CoutPad * 128u * (SG::SPLIT ? 2u : 1u);
       const char* w = reinterpret_cast<const char*>(p.wpack);
       for (int it = 0; it < nsteps; ++it) {
         const int s = it % FWD_STAGES;
         const uint32_t ph = (it / FWD_STAGES) & 1;
         mbar_wait(&tail->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&tail->full[s], bbytes);
-        bulk_g2s(smem + s * FWD_STAGE_BYTES + 16384, w + (size_t)it * bbytes, bbytes, &tail->full[s]);
+        bulk_g2s(smem + s * SG::BYTES + SG::B_OFF, w + (size_t)it * bbytes, bbytes, &tail->full[s]);
       }
     }
   } else {
@@ -140,12 +141,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
         const uint32_t ph = (it / FWD_STAGES) & 1;
         mbar_wait(&tail->full[s], ph);
         tc_fence_after();
-        const uint32_t a = smem_u32(smem + s * FWD_STAGE_BYTES);
-        const uint32_t b = a + 16384;
+        const uint32_t a = smem_u32(smem + s * SG::BYTES);
+        const uint32_t b = a + SG::B_OFF;
+        const uint32_t alo = a + SG::A_LO, blo = b + (uint32_t)p.CoutPad * 128u;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           umma<T>(tmem, make_sdesc(a + kk * 32, 16, 1024), make_sdesc(b + kk * 32, 16, 1024), idesc,
                   (uint32_t)((it | kk) != 0));
+          if (SG::SPLIT) {
+            umma<T>(tmem, make_sdesc(alo + kk * 32, 16, 1024), make_sdesc(b + kk * 32, 16, 1024), idesc, 1u);
+            umma<T>(tmem, make_sdesc(a + kk * 32, 16, 1024), make_sdesc(blo + kk * 32, 16, 1024), idesc, 1u);
+          }
         }
         tc_commit(&tail->empty[s]);
       }
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
   // ================================================================== epilogue (warps 0-7)
   const int ld_ep = p.CoutPad + 4;  // fp32 words per staged row (bank-conflict-free float4 rows)
   float* ep = reinterpret_cast<float*>(smem);
-  float* red = reinterpret_cast<float*>(smem + 128 * (128 + 4) * 4);  // [256][8] partial stats
+  double* red = reinterpret_cast<double*>(smem + 128 * (128 + 4) * 4);  // [256][8] partial stats (fp64)
   if (warp < 8) {
     mbar_wait(&tail->accum, 0);
     tc_fence_after();
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
   if (warp < 8) {
     const int nq = p.CoutPad >> 2;  // channel quads per row
     const bool do_stats = p.out_stats != nullptr;
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    double s1[4] = {0., 0., 0., 0.}, s2[4] = {0., 0., 0., 0.};
     const int nrows_out = grouped ? 32 : 128;
     const long rows_total = grouped ? (long)geom.M / 4 : (long)geom.M;
     for (int idx = tid; idx < nrows_out * nq; idx += 256) {
@@ -222,28 +228,31 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) conv_fwd_kernel(const __grid_c
       }
       if (grouped && p.pool_idx) *reinterpret_cast<uint32_t*>(p.pool_idx + grow * p.Cout + ch) = pidx;
       if (do_stats) {
-        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
-        s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+        s1[0] += (double)v.x; s1[1] += (double)v.y; s1[2] += (double)v.z; s1[3] += (double)v.w;
+        s2[0] += (double)v.x * v.x; s2[1] += (double)v.y * v.y; s2[2] += (double)v.z * v.z; s2[3] += (double)v.w * v.w;
       }
     }
     if (do_stats) {
       // host guarantees 256 % nq == 0 when out_stats != NULL -> every thread owns one channel quad
-      float4* rp = reinterpret_cast<float4*>(red + tid * 8);
-      rp[0] = make_float4(s1[0], s1[1], s1[2], s1[3]);
-      rp[1] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+      double* rp = red + tid * 8;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        rp[e] = s1[e];
+        rp[4 + e] = s2[e];
+      }
     }
   }
   __syncthreads();
   if (warp < 8 && p.out_stats != nullptr && tid < p.Cout) {
     const int nq = p.CoutPad >> 2;
     const int q = tid >> 2, e = tid & 3;
-    float a = 0.f, b = 0.f;
+    double a = 0., b = 0.;
     for (int t = q; t < 256; t += nq) {
       a += red[t * 8 + e];
       b += red[t * 8 + 4 + e];
     }
-    atomicAdd(p.out_stats + tid, (double)a);
-    atomicAdd(p.out_stats + p.Cout + tid, (double)b);
+    atomicAdd(p.out_stats + tid, a);
+    atomicAdd(p.out_stats + p.Cout + tid, b);
   }
   tc_fence_before();
   __syncthreads();
@@ -263,7 +272,7 @@ extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   int cin = 0;
   for (int s = 0; s < p->in.nseg; ++s) {
     if (p->in.seg[s].C % 32) return cunet_fail("conv_fwd: segment channels must be a multiple of 32");
-    if (p->in.bn_train && !p->in.seg[s].stats) return cunet_fail("conv_fwd: train-mode BN needs seg stats");
+    if (p->in.bn_train == 1 && !p->in.seg[s].stats) return cunet_fail("conv_fwd: train-mode BN needs seg stats");
     cin += p->in.seg[s].C;
   }
   if (cin > MAX_CIN) return cunet_fail("conv_fwd: too many input channels");
@@ -274,7 +283,8 @@ extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   const long M = (long)p->N * p->H * p->W;
   if (M <= 0) return 0;
   const long tiles = p->pool ? (M / 4 + 31) / 32 : (M + 127) / 128;
-  const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdSmemTail) + 1024;
+  const size_t smem = FWD_STAGES * (p->dtype == CUNET_BF16 ? StageGeom<bf16>::BYTES : StageGeom<float>::BYTES) +
+                      sizeof(FwdSmemTail) + 1024;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (p->dtype == CUNET_BF16) {

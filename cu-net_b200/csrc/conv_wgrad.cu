@@ -16,7 +16,6 @@
 namespace cunet {
 
 constexpr int WG_STAGES = 3;
-constexpr int WG_STAGE_BYTES = 32768;  // 16 KB activation sub-tiles + 16 KB gradient sub-tiles
 constexpr int WG_THREADS = 320;
 
 struct WgSmemTail {
@@ -37,13 +36,14 @@ template <typename T> struct WgGeom {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(WG_THREADS, 2) conv_wgrad_kernel(const __grid_constant__ cunet_conv_wgrad_params p,
+__global__ void __launch_bounds__(WG_THREADS, StageGeom<T>::MIN_CTAS) conv_wgrad_kernel(const __grid_constant__ cunet_conv_wgrad_params p,
                                                                     int nsplit, int npad) {
   using E = Elem<T>;
   using G = WgGeom<T>;
+  using SG = StageGeom<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  WgSmemTail* tail = reinterpret_cast<WgSmemTail*>(smem + WG_STAGES * SG::BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x;
@@ -119,23 +119,27 @@ __global__ void __launch_bounds__(WG_THREADS, 2) conv_wgrad_kernel(const __grid_
         }
       }
       mbar_wait(&tail->empty[s], ph ^ 1);
-      const uint32_t abase = smem_u32(smem + s * WG_STAGE_BYTES);
-      const uint32_t bbase = abase + 16384;
+      const uint32_t abase = smem_u32(smem + s * SG::BYTES);
+      const uint32_t bbase = abase + SG::B_OFF;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = ar0 + G::RPP * q;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if ((amask >> q) & 1) o = act_transform<T>(&tail->bn, ach, araw[q]);
-        sts128(abase + (acc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, acc & 7), o);
+        uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+        if ((amask >> q) & 1) o = act_transform<T>(&tail->bn, ach, araw[q], lo);
+        const uint32_t off = (acc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, acc & 7);
+        sts128(abase + off, o);
+        if (SG::SPLIT) sts128(abase + SG::A_LO + off, lo);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int idx = tid + 256 * q;
         if (idx < G::R * cprb) {
           const int r = idx / cprb, cc = idx - r * cprb;
-          uint4 o = make_uint4(0, 0, 0, 0);
-          if ((gmask >> q) & 1) o = grad_transform<T>(p.dy, &tail->gc, gco[q], graw[q]);
-          sts128(bbase + (cc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, cc & 7), o);
+          uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+          if ((gmask >> q) & 1) o = grad_transform<T>(p.dy, &tail->gc, gco[q], graw[q], lo);
+          const uint32_t off = (cc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, cc & 7);
+          sts128(bbase + off, o);
+          if (SG::SPLIT) sts128(bbase + 16384 + off, lo);
         }
       }
       fence_proxy_async();
@@ -152,12 +156,19 @@ __global__ void __launch_bounds__(WG_THREADS, 2) conv_wgrad_kernel(const __grid_
         const uint32_t ph = (it / WG_STAGES) & 1;
         mbar_wait(&tail->full[s], ph);
         tc_fence_after();
-        const uint32_t a = smem_u32(smem + s * WG_STAGE_BYTES);
-        const uint32_t b = a + 16384;
+        const uint32_t a = smem_u32(smem + s * SG::BYTES);
+        const uint32_t b = a + SG::B_OFF;
+        const uint32_t alo = a + SG::A_LO, blo = b + 16384u;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           umma<T>(tmem, make_sdesc_mn<T>(a + kk * KSTEP, G::SUB_BYTES), make_sdesc_mn<T>(b + kk * KSTEP, G::SUB_BYTES),
                   idesc, (uint32_t)((it | kk) != 0));
+          if (SG::SPLIT) {
+            umma<T>(tmem, make_sdesc_mn<T>(alo + kk * KSTEP, G::SUB_BYTES), make_sdesc_mn<T>(b + kk * KSTEP, G::SUB_BYTES),
+                    idesc, 1u);
+            umma<T>(tmem, make_sdesc_mn<T>(a + kk * KSTEP, G::SUB_BYTES), make_sdesc_mn<T>(blo + kk * KSTEP, G::SUB_BYTES),
+                    idesc, 1u);
+          }
         }
         tc_commit(&tail->empty[s]);
       }
@@ -176,11 +187,12 @@ __global__ void __launch_bounds__(WG_THREADS, 2) conv_wgrad_kernel(const __grid_
       float v[8];
       const int col = half * nhalf + j;
       tmem_ld8(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col, v);
-      if (k < Cin) {
+      const int dwc = p.dw_cin > 0 ? p.dw_cin : Cin;
+      if (k < dwc) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int co = col + e;
-          if (co < p.Cout) atomicAdd(p.dw + ((long)co * Cin + k) * p.taps + tap, v[e]);
+          if (co < p.Cout) atomicAdd(p.dw + ((long)co * dwc + k) * p.taps + tap, v[e]);
         }
       }
     }
@@ -200,7 +212,7 @@ extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) 
   int cin = 0;
   for (int s = 0; s < p->in.nseg; ++s) {
     if (p->in.seg[s].C % 32) return cunet_fail("conv_wgrad: segment channels must be a multiple of 32");
-    if (p->in.bn_train && !p->in.seg[s].stats) return cunet_fail("conv_wgrad: train-mode BN needs seg stats");
+    if (p->in.bn_train == 1 && !p->in.seg[s].stats) return cunet_fail("conv_wgrad: train-mode BN needs seg stats");
     cin += p->in.seg[s].C;
   }
   if (cin > MAX_CIN) return cunet_fail("conv_wgrad: too many input channels");
@@ -216,7 +228,8 @@ extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) 
   if (nsplit > total_steps) nsplit = total_steps;
   if (nsplit < 1) nsplit = 1;
   dim3 grid((unsigned)nsplit, (unsigned)ny);
-  const size_t smem = WG_STAGES * WG_STAGE_BYTES + sizeof(WgSmemTail) + 1024;
+  const size_t smem = WG_STAGES * (p->dtype == CUNET_BF16 ? StageGeom<bf16>::BYTES : StageGeom<float>::BYTES) +
+                      sizeof(WgSmemTail) + 1024;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (p->dtype == CUNET_BF16) {

@@ -13,6 +13,16 @@ namespace cunet {
 
 constexpr int MAX_CIN = 512;
 
+// Pipeline-stage layout shared by the GEMM kernels.  bf16: [A 16K][B 16K].  fp32 (3xTF32 split):
+// [A_hi 16K][A_lo 16K][B_hi ..][B_lo ..] (B hi/lo contiguous: one bulk copy brings both).
+template <typename T> struct StageGeom {
+  static constexpr bool SPLIT = Elem<T>::SPLIT;
+  static constexpr int BYTES = SPLIT ? 65536 : 32768;
+  static constexpr int A_LO = 16384;
+  static constexpr int B_OFF = SPLIT ? 32768 : 16384;
+  static constexpr int MIN_CTAS = SPLIT ? 1 : 2;
+};
+
 struct BnSmem {
   float scale[MAX_CIN];
   float shift[MAX_CIN];
@@ -20,6 +30,7 @@ struct BnSmem {
   float istd[MAX_CIN];
   int seg_start[CUNET_MAX_SEG + 1];
   int cin;
+  float floor;  // 0: ReLU;  -inf: identity input (bn_train == 2, the stem's im2col operand)
 };
 
 __device__ __forceinline__ int concat_cin(const cunet_concat& in) {
@@ -39,11 +50,15 @@ __device__ __forceinline__ void compute_bn_coefs(const cunet_concat& in, BnSmem*
     }
     for (int s = in.nseg; s <= CUNET_MAX_SEG; ++s) b->seg_start[s] = acc;
     b->cin = acc;
+    b->floor = in.bn_train == 2 ? -__int_as_float(0x7f800000) : 0.f;
   }
   const int Cin = concat_cin(in);
   for (int k = tid; k < kpad; k += nthreads) {
     float sc = 0.f, sh = 0.f, mu = 0.f, is = 0.f;
-    if (k < Cin) {
+    if (k < Cin && in.bn_train == 2) {
+      sc = 1.f;
+      is = 1.f;
+    } else if (k < Cin) {
       double mean, var;
       if (in.bn_train) {
         int s = 0, base = 0;
@@ -96,43 +111,48 @@ __device__ __forceinline__ bool act_issue(const cunet_concat& in, const BnSmem* 
 }
 
 template <typename T>
-__device__ __forceinline__ uint4 act_transform(const BnSmem* b, int ch, const uint4& raw) {
+__device__ __forceinline__ uint4 act_transform(const BnSmem* b, int ch, const uint4& raw, uint4& lo) {
   using E = Elem<T>;
   float f[E::EPC];
   Chunk<T>::unpack(raw, f);
+  const float fl = b->floor;
 #pragma unroll
-  for (int e = 0; e < E::EPC; ++e) f[e] = fmaxf(fmaf(f[e], b->scale[ch + e], b->shift[ch + e]), 0.f);
+  for (int e = 0; e < E::EPC; ++e) f[e] = fmaxf(fmaf(f[e], b->scale[ch + e], b->shift[ch + e]), fl);
+  if (E::SPLIT) lo = Chunk<T>::pack_lo(f);
   return Chunk<T>::pack_mma(f);
 }
 
 // ------------------------------------------------------------------------------------------------
 // gradient operand
+// dT = istd * (G - c1 - (T - mu) * c2),  c1 = mean(G),  c2 = istd * mean(G * xhat)   (centered form: no
+// cancellation between large q*T and r terms; see cunet_grad_src in the header)
 struct GradSmem {
-  float p[128];
-  float q[128];
-  float r[128];
+  float istd[128];
+  float c1[128];
+  float mu[128];
+  float c2[128];
 };
 
-// p, q, r of  dT = p*G + q*T + r  (see cunet_grad_src in the header)
+// gstats layout: [0,C) = sum G, [C,2C) = sum G * xhat  (xhat = (T - mean) * istd, accumulated centered by the
+// consumers' dgrad epilogues)
 __device__ __forceinline__ void compute_grad_coefs(const cunet_grad_src& gs, GradSmem* g, int tid, int nthreads) {
   for (int c = tid; c < 128; c += nthreads) {
-    float p = 1.f, q = 0.f, r = 0.f;
+    float istd = 1.f, c1 = 0.f, mu = 0.f, c2 = 0.f;
     if (gs.mode == 1 && c < gs.C) {
       const double n_inv = gs.inv_count;
       const double mean = gs.stats[c] * n_inv;
       double var = gs.stats[gs.C + c] * n_inv - mean * mean;
       if (var < 0.0) var = 0.0;
-      const double istd = 1.0 / sqrt(var + (double)gs.eps);
-      const double S1 = gs.gstats[c];
-      const double S2 = istd * (gs.gstats[gs.C + c] - mean * S1);  // sum G * xhat
-      const double qq = -istd * istd * S2 * n_inv;
-      p = (float)istd;
-      q = (float)qq;
-      r = (float)(-istd * S1 * n_inv - qq * mean);
+      const double is = 1.0 / sqrt(var + (double)gs.eps);
+      istd = (float)is;
+      c1 = (float)(gs.gstats[c] * n_inv);
+      mu = (float)mean;
+      c2 = (float)(is * gs.gstats[gs.C + c] * n_inv);
     }
-    g->p[c] = p;
-    g->q[c] = q;
-    g->r[c] = r;
+    g->istd[c] = istd;
+    g->c1[c] = c1;
+    g->mu[c] = mu;
+    g->c2[c] = c2;
   }
 }
 
@@ -168,7 +188,7 @@ __device__ __forceinline__ bool grad_issue(const cunet_grad_src& gs, int H, int 
 
 template <typename T>
 __device__ __forceinline__ uint4 grad_transform(const cunet_grad_src& gs, const GradSmem* gc, int co,
-                                                const GradRaw<T>& raw) {
+                                                const GradRaw<T>& raw, uint4& lo) {
   using E = Elem<T>;
   float g[E::EPC];
   Chunk<T>::unpack(raw.g, g);
@@ -176,7 +196,8 @@ __device__ __forceinline__ uint4 grad_transform(const cunet_grad_src& gs, const 
     float t[E::EPC];
     Chunk<T>::unpack(raw.t, t);
 #pragma unroll
-    for (int e = 0; e < E::EPC; ++e) g[e] = fmaf(gc->p[co + e], g[e], fmaf(gc->q[co + e], t[e], gc->r[co + e]));
+    for (int e = 0; e < E::EPC; ++e)
+      g[e] = gc->istd[co + e] * (g[e] - gc->c1[co + e] - (t[e] - gc->mu[co + e]) * gc->c2[co + e]);
   }
   if (gs.pooled) {
 #pragma unroll
@@ -185,6 +206,7 @@ __device__ __forceinline__ uint4 grad_transform(const cunet_grad_src& gs, const 
       if (id != raw.pos) g[e] = 0.f;
     }
   }
+  if (E::SPLIT) lo = Chunk<T>::pack_lo(g);
   return Chunk<T>::pack_mma(g);
 }
 

@@ -30,6 +30,7 @@ __global__ void pack_weights_kernel(const cunet_pack_desc* __restrict__ descs, i
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_fwd + n_dg; i += (long)gridDim.x * blockDim.x) {
     float f[E::EPC];
     char* dst;
+    long lo_off = 0;
     if (i < n_fwd) {
       // fwd image [tap][kb][co][8 chunks]
       const int cphys = (int)(i & 7);
@@ -44,7 +45,11 @@ __global__ void pack_weights_kernel(const cunet_pack_desc* __restrict__ descs, i
         const int k = kb * E::KBE + c * E::EPC + e;
         f[e] = (co < d.Cout && k < d.Cin) ? d.w[((long)co * d.Cin + k) * d.taps + tap] : 0.f;
       }
-      dst = reinterpret_cast<char*>(d.fwd) + i * 16;
+      // split mode: per (tap, kb) block the hi image (CoutPad rows) is followed by the lo image
+      const long blk = (long)tap * nkb + kb;
+      const long in_blk = ((long)co * 8 + cphys) * 16;
+      dst = reinterpret_cast<char*>(d.fwd) + blk * d.CoutPad * 128 * (E::SPLIT ? 2 : 1) + in_blk;
+      lo_off = (long)d.CoutPad * 128;
     } else {
       // dgrad image [chunk][kb][128 rows = input channel][8 chunks], K index = tap*coutk + co
       const long j = i - n_fwd;
@@ -62,9 +67,13 @@ __global__ void pack_weights_kernel(const cunet_pack_desc* __restrict__ descs, i
         const int tap = kg / coutk, co = kg - tap * coutk;
         f[e] = (tap < d.taps && co < d.Cout && k < d.Cin) ? d.w[((long)co * d.Cin + k) * d.taps + tap] : 0.f;
       }
-      dst = reinterpret_cast<char*>(d.dgrad) + j * 16;
+      const long blk = (long)chunk * nkbg + kb;
+      const long in_blk = ((long)row * 8 + cphys) * 16;
+      dst = reinterpret_cast<char*>(d.dgrad) + blk * 16384 * (E::SPLIT ? 2 : 1) + in_blk;
+      lo_off = 16384;
     }
     *reinterpret_cast<uint4*>(dst) = Chunk<T>::pack_mma(f);
+    if (E::SPLIT) *reinterpret_cast<uint4*>(dst + lo_off) = Chunk<T>::pack_lo(f);
   }
 }
 
@@ -73,13 +82,13 @@ using namespace cunet;
 
 extern "C" long cunet_pack_fwd_bytes(int Cin, int taps, int CoutPad, int dtype) {
   const int nkb = dtype == CUNET_BF16 ? PackGeom<bf16>::nkb_fwd(Cin) : PackGeom<float>::nkb_fwd(Cin);
-  return (long)taps * nkb * CoutPad * 128;
+  return (long)taps * nkb * CoutPad * 128 * (dtype == CUNET_BF16 ? 1 : 2);
 }
 extern "C" long cunet_pack_dgrad_bytes(int Cin, int taps, int CoutPad, int dtype) {
   // Cout is needed only for 3x3 (coutk = Cout = 32 in this network); pass CoutPad == Cout there.
   const int nkbg = dtype == CUNET_BF16 ? PackGeom<bf16>::nkb_dgrad(taps, CoutPad, CoutPad)
                                        : PackGeom<float>::nkb_dgrad(taps, CoutPad, CoutPad);
-  return (long)((Cin + 127) / 128) * nkbg * 128 * 128;
+  return (long)((Cin + 127) / 128) * nkbg * 128 * 128 * (dtype == CUNET_BF16 ? 1 : 2);
 }
 
 extern "C" int cunet_pack_weights(const cunet_pack_desc* descs_dev, int ndesc, int dtype, int max_chunks, void* stream) {

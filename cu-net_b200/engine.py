@@ -1,0 +1,430 @@
+"""Binds a Plan to device buffers and executes it through the C ABI (libcunet_b200.so).
+
+One Engine = one model replica on one GPU for one (batch, dtype).  All kernel parameter structs are built
+once (buffers never move), so a step is a fixed sequence of C-ABI launches on the current stream: safe to
+capture in a CUDA graph.  No PyTorch compute ops are on the step path (torch is used for allocation, zero
+fills and the NCCL process group only).
+
+HBM layout (all pixel-row / NHWC):
+  params   fp32 flat  : every conv weight [Cout][Cin][k][k] and BN weight/bias, reference order
+  grads    fp32 flat  : same layout (one contiguous allreduce bucket)
+  sq_avg   fp32 flat  : RMSprop state
+  bnbuf    fp32 flat  : BN running_mean / running_var
+  wpack    bytes      : tensor-core operand images of every conv (fwd + dgrad), rebuilt each step
+  acts     dtype      : one buffer per plan tensor [N*res*res][C]; heads fp32 [rows][head_pad]
+  G        dtype      : gradient accumulator per tensor (training)
+  zbuf     fp64       : per-tensor (sum, sumsq) and (sum G, sum G*T), loss, decode keys -- zeroed once per step
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from .plan import Plan
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _struct_array_to_device(structs, device):
+    raw = b"".join(bytes(s) for s in structs)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+class BnUpdateDesc(C.Structure):
+    _fields_ = [("stats", C.c_void_p * L.MAX_SEG), ("inv_count", C.c_double * L.MAX_SEG),
+                ("C", C.c_int * L.MAX_SEG), ("nseg", C.c_int), ("reps", C.c_int),
+                ("rmean", C.c_void_p), ("rvar", C.c_void_p), ("n_elems", C.c_double),
+                ("momentum", C.c_float), ("reserved", C.c_int)]
+
+
+class Engine(object):
+    def __init__(self, plan, batch, dtype="bf16", device=None, double_bn_update=True, share=None):
+        """share: another Engine of the same plan / dtype whose parameter storage (params, grads, optimizer
+        state, BN buffers) this engine reuses -- one model, several batch sizes."""
+        assert isinstance(plan, Plan)
+        L.load()
+        if not torch.cuda.is_available():
+            raise L.CunetError("cunet_b200 needs a CUDA device: there is no CPU fallback")
+        self.plan, self.N = plan, int(batch)
+        self.device = torch.device(device if device is not None else "cuda")
+        self.dtype = L.BF16 if dtype in ("bf16", torch.bfloat16) else L.F32
+        self.tdtype = torch.bfloat16 if self.dtype == L.BF16 else torch.float32
+        self.double_bn_update = double_bn_update
+        self.grad_scale = 1.0          # 1 / world_size under data parallelism
+        dev = self.device
+        p = plan
+
+        # ---- parameters
+        off = 0
+        boff = 0
+        self.p_off, self.b_off, self.cnt_idx = {}, {}, {}
+        for s in p.params:
+            if s.kind in ("conv", "bn_weight", "bn_bias"):
+                self.p_off[s.name] = (off, s.numel, s.shape)
+                off += (s.numel + 3) // 4 * 4                      # keep every tensor 16-byte aligned
+            elif s.kind in ("bn_mean", "bn_var"):
+                self.b_off[s.name] = (boff, s.numel, s.shape)
+                boff += (s.numel + 3) // 4 * 4
+            else:
+                self.cnt_idx[s.name] = len(self.cnt_idx)
+        self.n_params = off
+        if share is not None:
+            assert share.n_params == off and share.dtype == self.dtype
+            self.params, self.grads, self.sq_avg = share.params, share.grads, share.sq_avg
+            self.bnbuf, self.counters, self.lr = share.bnbuf, share.counters, share.lr
+        else:
+            self.params = torch.zeros(off, device=dev)
+            self.grads = torch.zeros(off, device=dev)
+            self.sq_avg = torch.zeros(off, device=dev)
+            self.bnbuf = torch.zeros(boff, device=dev)
+            self.counters = torch.zeros(len(self.cnt_idx), dtype=torch.long, device=dev)
+            for name, (o, n, _) in self.b_off.items():
+                if name.endswith("running_var"):
+                    self.bnbuf[o:o + n] = 1.0
+            self.lr = torch.zeros(1, device=dev)
+
+        # ---- activations, gradient accumulators, statistics
+        N = self.N
+        self.act, self.G, self.pidx = {}, {}, {}
+        zoff = 0
+        self.stat_off, self.gstat_off = {}, {}
+        for t in p.tensors.values():
+            rows = N * t.res * t.res
+            self.act[t.name] = torch.empty(rows, t.C, device=dev, dtype=torch.float32 if t.fp32 else self.tdtype)
+            self.stat_off[t.name] = zoff
+            zoff += 2 * t.C
+            self.gstat_off[t.name] = zoff
+            zoff += 2 * t.C
+            if t.fp32:
+                self.G[t.name] = torch.zeros(rows, t.C, device=dev, dtype=self.tdtype)   # dLoss/dhead
+            elif t.name != "stem.y":
+                self.G[t.name] = torch.empty(rows, t.C, device=dev, dtype=self.tdtype)
+        for op in p.ops:
+            if op.pool:
+                self.pidx[op.out.name] = torch.empty(N * (op.res // 2) ** 2, op.cout, device=dev, dtype=torch.uint8)
+        self.nheads = len(p.heads)
+        self.loss_off = zoff
+        zoff += 1 + self.nheads
+        self.keys_off = zoff
+        zoff += N * p.class_num
+        self.zbuf = torch.zeros(zoff, dtype=torch.float64, device=dev)
+        self.preds = torch.zeros(N, p.class_num, 2, device=dev)
+        self.target = torch.zeros(N, p.class_num, p.out_res, p.out_res, device=dev)
+        self.img = torch.zeros(N, 3, p.in_res, p.in_res, device=dev)
+        self.cols = torch.empty(N * p.stem_res ** 2, 160, device=dev, dtype=self.tdtype)
+        self.dy0 = torch.empty(N * p.stem_res ** 2, p.C0, device=dev, dtype=self.tdtype)
+
+        # ---- packed weights
+        descs, woff = [], 0
+        self.wfwd, self.wdg = {}, {}
+        plist = [("features.conv0", 147, 1, p.C0, p.C0, False)]
+        for op in p.ops:
+            plist.append((op.conv, op.cin, op.taps, op.cout, op.cout_pad, True))
+        sizes = []
+        for name, cin, taps, cout, cpad, need_dg in plist:
+            nf = L.pack_fwd_bytes(cin, taps, cpad, self.dtype)
+            nd = L.pack_dgrad_bytes(cin, taps, cpad, self.dtype) if need_dg else 0
+            sizes.append((woff, nf, nd))
+            woff += nf + nd
+        self.wpack = torch.zeros(woff, dtype=torch.uint8, device=dev)
+        base = self.wpack.data_ptr()
+        for (name, cin, taps, cout, cpad, need_dg), (o, nf, nd) in zip(plist, sizes):
+            self.wfwd[name] = base + o
+            self.wdg[name] = base + o + nf if need_dg else None
+            wptr = self.params.data_ptr() + 4 * self.p_off[name + ".weight"][0]
+            descs.append(L.PackDesc(wptr, base + o, (base + o + nf) if need_dg else None, cout, cin, taps, cpad))
+        self.pack_descs = _struct_array_to_device(descs, dev)
+        self.n_pack = len(descs)
+
+        self._build_calls()
+
+    # ------------------------------------------------------------------------------------------ pointers
+    def _pp(self, name):
+        return self.params.data_ptr() + 4 * self.p_off[name][0]
+
+    def _gp(self, name):
+        return self.grads.data_ptr() + 4 * self.p_off[name][0]
+
+    def _bp(self, name):
+        return self.bnbuf.data_ptr() + 4 * self.b_off[name][0]
+
+    def _stats(self, tname):
+        return self.zbuf.data_ptr() + 8 * self.stat_off[tname]
+
+    def _gstats(self, tname):
+        return self.zbuf.data_ptr() + 8 * self.gstat_off[tname]
+
+    def _concat(self, cc, op, mode):
+        """mode: 1 train, 0 eval."""
+        cc.nseg = len(op.srcs)
+        for i, (t, up) in enumerate(op.srcs):
+            s = cc.seg[i]
+            s.ptr = self.act[t.name].data_ptr()
+            s.stats = self._stats(t.name)
+            s.inv_count = 1.0 / (self.N * t.res * t.res)
+            s.C, s.ld, s.up = t.C, t.C, int(up)
+        cc.bn_train = mode
+        cc.gamma, cc.beta = self._pp(op.norm + ".weight"), self._pp(op.norm + ".bias")
+        cc.rmean, cc.rvar = self._bp(op.norm + ".running_mean"), self._bp(op.norm + ".running_var")
+        cc.eps = BN_EPS
+
+    def _grad_src(self, gs, t, op):
+        """Gradient of tensor t = output of op."""
+        gs.g = self.G[t.name].data_ptr()
+        gs.C, gs.ld = t.C, t.C
+        gs.eps = BN_EPS
+        if t.fp32:                       # head: plain dLoss/dhead
+            gs.mode, gs.pooled = 0, 0
+            gs.t = gs.stats = gs.gstats = gs.pool_idx = None
+            gs.inv_count = 1.0
+        else:
+            gs.mode = 1
+            gs.t = self.act[t.name].data_ptr()
+            gs.stats, gs.gstats = self._stats(t.name), self._gstats(t.name)
+            gs.inv_count = 1.0 / (self.N * t.res * t.res)
+            gs.pooled = int(op.pool)
+            gs.pool_idx = self.pidx[t.name].data_ptr() if op.pool else None
+
+    # ------------------------------------------------------------------------------------------ launch lists
+    def _build_calls(self):
+        p, N, lib = self.plan, self.N, L.load()
+        self._keep = []
+
+        def fwd_list(mode):
+            calls = []
+            # stem
+            sp = L.ConvFwdParams()
+            sp.inp.nseg = 1
+            sp.inp.seg[0].ptr = self.cols.data_ptr()
+            sp.inp.seg[0].C, sp.inp.seg[0].ld, sp.inp.seg[0].up = 160, 160, 0
+            sp.inp.seg[0].inv_count = 1.0
+            sp.inp.bn_train = 2
+            sp.N, sp.H, sp.W, sp.taps = N, p.stem_res, p.stem_res, 1
+            sp.wpack, sp.Cout, sp.CoutPad = self.wfwd["features.conv0"], p.C0, p.C0
+            sp.out, sp.out_ld, sp.out_fp32 = self.act["stem.y"].data_ptr(), p.C0, 0
+            sp.out_stats = self._stats("stem.y") if mode else None
+            sp.pool, sp.pool_idx, sp.dtype = 0, None, self.dtype
+            calls.append((lib.cunet_conv_fwd, sp))
+            pp = L.StemPoolParams()
+            pp.y, pp.y_stats = self.act["stem.y"].data_ptr(), self._stats("stem.y")
+            pp.gamma, pp.beta = self._pp("features.norm0.weight"), self._pp("features.norm0.bias")
+            pp.rmean, pp.rvar = self._bp("features.norm0.running_mean"), self._bp("features.norm0.running_var")
+            pp.x = self.act["stem.x"].data_ptr()
+            pp.x_stats = self._stats("stem.x") if mode else None
+            pp.N, pp.H, pp.W = N, p.stem_res, p.stem_res
+            pp.bn_train, pp.eps, pp.dtype = mode, BN_EPS, self.dtype
+            calls.append((lib.cunet_stem_pool_fwd, pp))
+            for op in p.ops:
+                cp = L.ConvFwdParams()
+                self._concat(cp.inp, op, mode)
+                cp.N, cp.H, cp.W, cp.taps = N, op.res, op.res, op.taps
+                cp.wpack, cp.Cout, cp.CoutPad = self.wfwd[op.conv], op.cout, op.cout_pad
+                cp.out, cp.out_ld = self.act[op.out.name].data_ptr(), op.out.C
+                cp.out_fp32 = int(op.kind == "head")
+                cp.out_stats = self._stats(op.out.name) if (mode and op.kind != "head") else None
+                cp.pool = int(op.pool)
+                cp.pool_idx = self.pidx[op.out.name].data_ptr() if op.pool else None
+                cp.dtype = self.dtype
+                calls.append((lib.cunet_conv_fwd, cp))
+            return calls
+
+        self.fwd_train, self.fwd_eval = fwd_list(1), fwd_list(0)
+
+        # BN running statistics (one launch)
+        upd = []
+        d = BnUpdateDesc()
+        d.stats[0], d.inv_count[0], d.C[0], d.nseg = self._stats("stem.y"), 1.0 / (N * p.stem_res ** 2), p.C0, 1
+        d.reps, d.n_elems, d.momentum = 1, float(N * p.stem_res ** 2), BN_MOMENTUM
+        d.rmean, d.rvar = self._bp("features.norm0.running_mean"), self._bp("features.norm0.running_var")
+        upd.append(d)
+        incr = torch.zeros(len(self.cnt_idx), dtype=torch.long)
+        incr[self.cnt_idx["features.norm0.num_batches_tracked"]] = 1
+        for op in p.ops:
+            d = BnUpdateDesc()
+            d.nseg = len(op.srcs)
+            for i, (t, up) in enumerate(op.srcs):
+                d.stats[i], d.inv_count[i], d.C[i] = self._stats(t.name), 1.0 / (N * t.res * t.res), t.C
+            d.reps = 2 if (op.checkpointed and self.double_bn_update) else 1
+            d.n_elems, d.momentum = float(N * op.res * op.res), BN_MOMENTUM
+            d.rmean, d.rvar = self._bp(op.norm + ".running_mean"), self._bp(op.norm + ".running_var")
+            upd.append(d)
+            incr[self.cnt_idx[op.norm + ".num_batches_tracked"]] = d.reps
+        self.bn_descs = _struct_array_to_device(upd, self.device)
+        self.n_bn = len(upd)
+        self.counter_incr = incr.to(self.device)
+
+        # loss
+        def mse_params(with_grad):
+            mp = L.MseParams()
+            for k, h in enumerate(p.heads):
+                mp.heads[k] = self.act[h.name].data_ptr()
+                mp.dheads[k] = self.G[h.name].data_ptr() if with_grad else None
+            mp.nheads = self.nheads
+            mp.target = self.target.data_ptr()
+            mp.N, mp.C, mp.H, mp.W, mp.ld = N, p.class_num, p.out_res, p.out_res, p.head_pad
+            mp.loss = self.zbuf.data_ptr() + 8 * self.loss_off
+            mp.keys = self.zbuf.data_ptr() + 8 * self.keys_off
+            mp.grad_scale, mp.dtype = 1.0, self.dtype
+            return mp
+        self.mse_train, self.mse_eval = mse_params(True), mse_params(False)
+
+        # backward
+        calls = []
+        for op, flags in p.backward_schedule():
+            dp = L.ConvDgradParams()
+            self._concat(dp.inp, op, 1)
+            for i, ((t, up), (acc, last)) in enumerate(zip(op.srcs, flags)):
+                dp.gacc[i].G = self.G[t.name].data_ptr()
+                dp.gacc[i].gstats = self._gstats(t.name) if last else None
+                dp.gacc[i].ld, dp.gacc[i].accumulate = t.C, int(acc)
+            self._grad_src(dp.dy, op.out, op)
+            dp.N, dp.H, dp.W, dp.taps = N, op.res, op.res, op.taps
+            dp.wpack_dgrad, dp.Cout, dp.CoutPad = self.wdg[op.conv], op.cout, op.cout_pad
+            dp.dgamma, dp.dbeta = self._gp(op.norm + ".weight"), self._gp(op.norm + ".bias")
+            dp.dtype = self.dtype
+            calls.append((lib.cunet_conv_dgrad, dp))
+            wp = L.ConvWgradParams()
+            self._concat(wp.inp, op, 1)
+            self._grad_src(wp.dy, op.out, op)
+            wp.N, wp.H, wp.W, wp.taps, wp.Cout = N, op.res, op.res, op.taps, op.cout
+            wp.dw, wp.nsplit, wp.dtype, wp.dw_cin = self._gp(op.conv + ".weight"), 0, self.dtype, 0
+            calls.append((lib.cunet_conv_wgrad, wp))
+        # stem backward: parameter-gradient reduction, dy, conv0 wgrad
+        for phase in (0, 1):
+            sb = L.StemBwdParams()
+            sb.y, sb.y_stats = self.act["stem.y"].data_ptr(), self._stats("stem.y")
+            sb.gamma, sb.beta = self._pp("features.norm0.weight"), self._pp("features.norm0.bias")
+            sx = p.stem_x
+            sb.dx.g, sb.dx.t = self.G["stem.x"].data_ptr(), self.act["stem.x"].data_ptr()
+            sb.dx.stats, sb.dx.gstats = self._stats("stem.x"), self._gstats("stem.x")
+            sb.dx.pool_idx, sb.dx.inv_count = None, 1.0 / (N * sx.res * sx.res)
+            sb.dx.C, sb.dx.ld, sb.dx.mode, sb.dx.pooled, sb.dx.eps = sx.C, sx.C, 1, 0, BN_EPS
+            sb.dgamma, sb.dbeta = self._gp("features.norm0.weight"), self._gp("features.norm0.bias")
+            sb.dy = self.dy0.data_ptr()
+            sb.N, sb.H, sb.W, sb.eps, sb.dtype, sb.phase = N, p.stem_res, p.stem_res, BN_EPS, self.dtype, phase
+            calls.append((lib.cunet_stem_bwd, sb))
+        wp = L.ConvWgradParams()
+        wp.inp.nseg = 1
+        wp.inp.seg[0].ptr, wp.inp.seg[0].C, wp.inp.seg[0].ld = self.cols.data_ptr(), 160, 160
+        wp.inp.seg[0].inv_count = 1.0
+        wp.inp.bn_train = 2
+        wp.dy.g, wp.dy.C, wp.dy.ld, wp.dy.mode, wp.dy.pooled = self.dy0.data_ptr(), p.C0, p.C0, 0, 0
+        wp.dy.inv_count = 1.0
+        wp.N, wp.H, wp.W, wp.taps, wp.Cout = N, p.stem_res, p.stem_res, 1, p.C0
+        wp.dw, wp.nsplit, wp.dtype, wp.dw_cin = self._gp("features.conv0.weight"), 0, self.dtype, 147
+        calls.append((lib.cunet_conv_wgrad, wp))
+        self.bwd_calls = calls
+
+    # ------------------------------------------------------------------------------------------ execution
+    def _run(self, calls):
+        st = L.stream_ptr()
+        for fn, prm in calls:
+            rc = fn(C.byref(prm), st)
+            if rc != 0:
+                L.check(rc, fn.__name__)
+
+    def pack_weights(self):
+        L.pack_weights(self.pack_descs.data_ptr(), self.n_pack, self.dtype)
+
+    def forward(self, train):
+        """img must already be in self.img.  Leaves the head outputs in self.act[head]."""
+        lib = L.load()
+        self.pack_weights()
+        L.check(lib.cunet_stem_im2col(C.c_void_p(self.img.data_ptr()), C.c_void_p(self.cols.data_ptr()), self.N,
+                                      self.plan.in_res, self.plan.in_res, self.dtype, L.stream_ptr()), "stem_im2col")
+        if train:
+            self.zbuf.zero_()
+        self._run(self.fwd_train if train else self.fwd_eval)
+        if train:
+            L.check(lib.cunet_bn_running_update(C.c_void_p(self.bn_descs.data_ptr()), self.n_bn, L.stream_ptr()),
+                    "bn_running_update")
+            self.counters.add_(self.counter_incr)
+
+    def loss_and_decode(self, with_grad):
+        """target must already be in self.target. loss -> zbuf[loss_off], preds -> self.preds."""
+        lib = L.load()
+        mp = self.mse_train if with_grad else self.mse_eval
+        mp.grad_scale = self.grad_scale
+        if not with_grad:
+            self.zbuf[self.loss_off:].zero_()
+        L.check(lib.cunet_mse_decode(C.byref(mp), L.stream_ptr()), "mse_decode")
+        L.check(lib.cunet_decode_finalize(C.c_void_p(self.zbuf.data_ptr() + 8 * self.keys_off),
+                                          C.c_void_p(self.preds.data_ptr()), self.N * self.plan.class_num,
+                                          self.plan.out_res, L.stream_ptr()), "decode_finalize")
+
+    def backward(self):
+        """dLoss/dhead must be in self.G[head] (written by loss_and_decode or by the autograd bridge)."""
+        self.grads.zero_()
+        self._run(self.bwd_calls)
+
+    def optimizer_step(self, alpha=0.99, eps=1e-8):
+        lib = L.load()
+        L.check(lib.cunet_rmsprop_step(C.c_void_p(self.params.data_ptr()), C.c_void_p(self.grads.data_ptr()),
+                                       C.c_void_p(self.sq_avg.data_ptr()), C.c_long(self.n_params),
+                                       C.c_void_p(self.lr.data_ptr()), C.c_float(alpha), C.c_float(eps),
+                                       L.stream_ptr()), "rmsprop_step")
+
+    def loss_value(self):
+        return self.zbuf[self.loss_off].clone()
+
+    def head_outputs(self):
+        """loss_num views shaped like the reference's outputs: [N, class_num, H, W] (NCHW view of NHWC)."""
+        p = self.plan
+        outs = []
+        for h in p.heads:
+            a = self.act[h.name].view(self.N, p.out_res, p.out_res, p.head_pad)[..., :p.class_num]
+            outs.append(a.permute(0, 3, 1, 2))
+        return outs
+
+    # kernels launched per call, for bench.py's gpu_launches
+    def launches_per_train_step(self):
+        return 2 + len(self.fwd_train) + 1 + 2 + len(self.bwd_calls) + 1
+
+
+class Trainer(object):
+    """Fused training / evaluation steps on one GPU (one process per GPU under data parallelism).
+
+    train_step = H2D(img, heatmap) -> forward -> multi-loss MSE + decode -> backward -> [NCCL allreduce of the
+    flat gradient bucket] -> RMSprop -> (weights re-packed at the start of the next step).
+    Mirrors train() of the reference (cu-net.py:147-206) with the per-iteration .cpu() metric loops replaced by
+    the fused on-device decode.
+    """
+
+    def __init__(self, net, batch, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, process_group=None,
+                 world_size=1):
+        self.net = net
+        self.eng = net.engine(batch, device)
+        self.alpha, self.eps = alpha, eps
+        self.set_lr(lr)
+        self.pg, self.world = process_group, world_size
+        self.eng.grad_scale = 1.0 / world_size
+
+    def set_lr(self, lr):
+        self.eng.lr.fill_(lr)
+
+    def load_batch(self, img, heatmap):
+        """Copy one batch into the engine's static input buffers (pinned host or device tensors)."""
+        self.eng.img.copy_(img, non_blocking=True)
+        self.eng.target.copy_(heatmap, non_blocking=True)
+
+    def train_step(self, img=None, heatmap=None):
+        e = self.eng
+        if img is not None:
+            self.load_batch(img, heatmap)
+        e.forward(train=True)
+        e.loss_and_decode(with_grad=True)
+        e.backward()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(e.grads, group=self.pg)       # gradients were pre-scaled by 1/world (sum == mean)
+        e.optimizer_step(self.alpha, self.eps)
+        return e.loss_value()
+
+    def eval_step(self, img=None, heatmap=None):
+        e = self.eng
+        if img is not None:
+            self.load_batch(img, heatmap)
+        e.forward(train=False)
+        e.loss_and_decode(with_grad=False)
+        return e.loss_value(), e.preds

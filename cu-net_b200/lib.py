@@ -59,7 +59,29 @@ class ConvDgradParams(C.Structure):
 class ConvWgradParams(C.Structure):
     _fields_ = [("inp", Concat), ("dy", GradSrc),
                 ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
-                ("Cout", C.c_int), ("dw", C.c_void_p), ("nsplit", C.c_int), ("dtype", C.c_int)]
+                ("Cout", C.c_int), ("dw", C.c_void_p), ("nsplit", C.c_int), ("dtype", C.c_int),
+                ("dw_cin", C.c_int), ("reserved", C.c_int)]
+
+
+class StemPoolParams(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("y_stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("rmean", C.c_void_p), ("rvar", C.c_void_p), ("x", C.c_void_p), ("x_stats", C.c_void_p),
+                ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("bn_train", C.c_int), ("eps", C.c_float),
+                ("dtype", C.c_int)]
+
+
+class StemBwdParams(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("y_stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("dx", GradSrc), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dy", C.c_void_p),
+                ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("eps", C.c_float), ("dtype", C.c_int),
+                ("phase", C.c_int)]
+
+
+class MseParams(C.Structure):
+    _fields_ = [("heads", C.c_void_p * 16), ("dheads", C.c_void_p * 16), ("nheads", C.c_int),
+                ("target", C.c_void_p), ("N", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("ld", C.c_int), ("loss", C.c_void_p), ("keys", C.c_void_p), ("grad_scale", C.c_float),
+                ("dtype", C.c_int)]
 
 
 class PackDesc(C.Structure):
@@ -92,7 +114,9 @@ def load():
 # every symbol include/cunet_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "cunet_last_error", "cunet_abi_version",
-    "cunet_conv_fwd", "cunet_conv_dgrad", "cunet_conv_wgrad", "cunet_pack_weights", "cunet_pack_fwd_bytes", "cunet_pack_dgrad_bytes",
+    "cunet_conv_fwd", "cunet_conv_dgrad", "cunet_conv_wgrad", "cunet_pack_weights", "cunet_pack_fwd_bytes",
+    "cunet_pack_dgrad_bytes", "cunet_stem_im2col", "cunet_stem_pool_fwd", "cunet_stem_bwd", "cunet_mse_decode",
+    "cunet_decode_finalize", "cunet_bn_running_update", "cunet_rmsprop_step",
 ]
 
 

@@ -43,7 +43,8 @@ typedef struct {
 typedef struct {
   cunet_seg seg[CUNET_MAX_SEG];
   int nseg;
-  int bn_train;       /* 1: batch statistics from seg[].stats; 0: running statistics */
+  int bn_train;       /* 1: batch statistics from seg[].stats; 0: running statistics;
+                         2: identity (no BatchNorm, no ReLU: the stem's im2col operand) */
   const float* gamma; /* [Cin] BN weight, concat order                 */
   const float* beta;  /* [Cin] BN bias                                 */
   const float* rmean; /* [Cin] running mean  (eval mode)               */
@@ -78,15 +79,15 @@ int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream);
  * Every tensor of the network is consumed only through BatchNorm'd convs, so its gradient is
  *   dT = istd * (G - mean(G) - xhat * mean(G*xhat)),   G = sum over consumers of gamma_j * dz_j
  * (autograd of nn.BatchNorm2d train mode, summed over the consumers that share T's batch statistics).
- * The dgrad kernels of the consumers accumulate G and (sum G, sum G*T); the producer's backward kernels
- * evaluate dT on the fly as  p*G + q*T + r  per channel.  mode 0: dT = g (plain, e.g. dLoss/dhead).
+ * The dgrad kernels of the consumers accumulate G and (sum G, sum G*xhat); the producer's backward kernels
+ * evaluate dT on the fly per channel.  mode 0: dT = g (plain, e.g. dLoss/dhead).
  * pooled = 1: T is the 2x2-maxpooled conv output (g, t, pool_idx at half resolution); the gradient is
  * routed to the argmax position (autograd of nn.MaxPool2d, models/cu_net.py:249,260). */
 typedef struct {
   const void* g;
   const void* t;
   const double* stats;     /* [2*C] sum, sumsq of T (forward)         */
-  const double* gstats;    /* [2*C] sum G, sum G*T                     */
+  const double* gstats;    /* [2*C] sum G, sum G*xhat                  */
   const uint8_t* pool_idx; /* [rows][C] or NULL                        */
   double inv_count;        /* 1 / rows of T                            */
   int C, ld;
@@ -99,7 +100,7 @@ typedef struct {
 /* Per-source accumulator written by a consumer's dgrad epilogue. */
 typedef struct {
   void* G;        /* [rows][ld] dtype; NULL: this source needs no gradient  */
-  double* gstats; /* non-NULL: this is the last consumer -> accumulate (sum G, sum G*T) of the final G */
+  double* gstats; /* non-NULL: this is the last consumer -> accumulate (sum G, sum G*xhat) of the final G */
   int ld;
   int accumulate; /* 0: first consumer in backward order (write), 1: read-modify-write */
 } cunet_gacc;
@@ -132,9 +133,88 @@ typedef struct {
   float* dw;               /* [Cout][Cin][taps] fp32, atomically accumulated */
   int nsplit;              /* CTAs along the pixel dimension (0: library default) */
   int dtype;
+  int dw_cin;              /* row length (Cin) of dw; 0: the concat's channel count.  Channels >= dw_cin are padding */
+  int reserved;
 } cunet_conv_wgrad_params;
 
 int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream);
+
+/* ---- stem: conv0 7x7 s2 p3 -> norm0 -> relu0 -> pool0 (models/cu_net.py:299-304) ------------------
+ * conv0 runs on the tensor cores through cunet_conv_fwd / cunet_conv_wgrad with an identity input
+ * (bn_train == 2) over an im2col matrix [N*Ho*Wo][160] (147 = 3*7*7 columns in the reference's
+ * weight-flattening order c*49 + kh*7 + kw, zero padded to 160). */
+int cunet_stem_im2col(const float* img /* [N][3][Hi][Wi] fp32, NCHW as the reference feeds it */,
+                      void* cols /* [N*Ho*Wo][160] dtype */, int N, int Hi, int Wi, int dtype, void* stream);
+
+/* norm0 -> relu0 -> pool0 forward: y [N*H*W][128] -> x [N*H/2*W/2][128], accumulating the statistics of x.
+ * bn_train: 1 batch statistics from y_stats, 0 running statistics. */
+typedef struct {
+  const void* y;
+  const double* y_stats; /* [256] sum, sumsq of y (train) */
+  const float* gamma; const float* beta; const float* rmean; const float* rvar; /* [128] norm0 */
+  void* x;
+  double* x_stats;       /* [256] += */
+  int N, H, W;           /* resolution of y */
+  int bn_train;
+  float eps;
+  int dtype;
+} cunet_stem_pool_params;
+int cunet_stem_pool_fwd(const cunet_stem_pool_params* p, void* stream);
+
+/* Backward of pool0 / relu0 / norm0 (autograd of nn.MaxPool2d, nn.ReLU, nn.BatchNorm2d train mode).
+ * phase 0: dgamma0 += sum dz*yhat, dbeta0 += sum dz      (dz = gradient w.r.t. norm0's output)
+ * phase 1: dy = gamma*istd*(dz - dbeta0/n - yhat*dgamma0/n)  written as [N*H*W][128] dtype
+ * The gradient of x arrives in the batch-norm backward form (cunet_grad_src mode 1). */
+typedef struct {
+  const void* y;
+  const double* y_stats;
+  const float* gamma; const float* beta;
+  cunet_grad_src dx;     /* gradient of x (pooled resolution), mode 1 */
+  float* dgamma; float* dbeta; /* [128] fp32 (phase 0: accumulated; phase 1: read) */
+  void* dy;              /* phase 1 output */
+  int N, H, W;
+  float eps;
+  int dtype;
+  int phase;
+} cunet_stem_bwd_params;
+int cunet_stem_bwd(const cunet_stem_bwd_params* p, void* stream);
+
+/* ---- loss + decode ------------------------------------------------------------------------------
+ * Multi-loss MSE  sum_k mean((out_k - heatmap)^2)  (cu-net.py:175-178) with its gradient, fused with the
+ * argmax landmark decode of the last head (pylib/Evaluation.py:6-23: first maximum, 1-based (x, y),
+ * zero where max <= 0).  Heads are NHWC fp32 [N*H*W][ld]; the target is NCHW fp32 [N][C][H][W]. */
+typedef struct {
+  const float* heads[16]; /* loss_num head outputs */
+  void* dheads[16];       /* gradients [N*H*W][ld] dtype, or all NULL (loss / decode only) */
+  int nheads;
+  const float* target;
+  int N, C, H, W, ld;
+  double* loss;           /* [1 + nheads]: total, then per head; accumulated (+=) */
+  unsigned long long* keys; /* [N*C] zero-initialised scratch for the decode */
+  float grad_scale;       /* multiplies the gradient (1 / world_size under data parallelism) */
+  int dtype;
+} cunet_mse_params;
+int cunet_mse_decode(const cunet_mse_params* p, void* stream);
+/* keys -> preds [N][C][2] fp32 (x, y) 1-based, masked by max > 0 */
+int cunet_decode_finalize(const unsigned long long* keys, float* preds, int NC, int W, void* stream);
+
+/* ---- BatchNorm running statistics (nn.BatchNorm2d momentum update) ---------- */
+typedef struct {
+  const double* stats[CUNET_MAX_SEG]; /* per segment [2*C] */
+  double inv_count[CUNET_MAX_SEG];
+  int C[CUNET_MAX_SEG];
+  int nseg;
+  int reps;          /* 1, or 2 for BatchNorms that the reference re-runs under checkpointing */
+  float* rmean; float* rvar;  /* [Cin] */
+  double n_elems;    /* elements per channel seen by this BatchNorm (for the unbiased variance) */
+  float momentum;
+  int reserved;
+} cunet_bn_update_desc;
+int cunet_bn_running_update(const cunet_bn_update_desc* descs_dev, int ndesc, void* stream);
+
+/* ---- optimizer: torch.optim.RMSprop(lr, alpha, eps, momentum=0, weight_decay=0) (cu-net.py:60-61) ---- */
+int cunet_rmsprop_step(float* params, const float* grads, float* square_avg, long n, const float* lr_dev,
+                       float alpha, float eps, void* stream);
 
 /* Weight packing: reference-layout fp32 master weights -> tensor-core operand images.
  * One descriptor per conv; all descriptors processed by one launch.
