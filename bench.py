@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- CU-Net training-step throughput on B200 (images/sec), with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cunet8|cunet2|cunet16] [--impl reference]
+
+One JSON line on stdout (rank 0).  A "step" is one full training step of the reference's train() loop
+(cu-net.py:147-206) on one batch of synthetic input: forward, multi-loss MSE (+ fused landmark decode), backward,
+[gradient allreduce], RMSprop.  `value` times it with the batch already resident in HBM; `e2e` times the same
+step through the public Trainer API with pinned HOST buffers (H2D of image+heatmap and D2H of the loss inside the
+timed region).  `--impl reference` times the reference's own algorithm on the host CPU cores (the oracle port of
+models/cu_net.py -- /root/reference is not present on the GPU box) for the same config and metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[2] / [1] / [4]; batch = per-GPU batch (weak scaling, stated in the JSON line)
+    "cunet8": dict(layer_num=8, order=1, loss_num=8, class_num=68, batch=24, dtype="bf16"),
+    "cunet2": dict(layer_num=2, order=1, loss_num=2, class_num=68, batch=24, dtype="fp32"),
+    "cunet16": dict(layer_num=16, order=1, loss_num=16, class_num=16, batch=16, dtype="bf16"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def cpu_reference(cfg, sample_batch, iters, warmup=1):
+    """The reference's algorithm (oracle port of models/cu_net.py + cu-net.py:175-183 loss/backward/RMSprop) on
+    the host cores.  Returns (images_per_sec, cores)."""
+    import torch
+    from oracle import cunet_oracle, synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = cunet_oracle.init_state(cfg["class_num"], cfg["layer_num"], cfg["order"], seed=0)
+    net = cunet_oracle.OracleCUNet(state, cfg["class_num"], cfg["layer_num"], cfg["order"], cfg["loss_num"])
+    img, hm = synthetic.make_inputs(sample_batch, cfg["class_num"], seed=0)
+    params = net.parameters()
+    sq = [torch.zeros_like(p) for p in params]
+    times = []
+    for it in range(warmup + iters):
+        t0 = time.perf_counter()
+        net.zero_grad()
+        loss = cunet_oracle.multi_loss_mse(net(img), hm)
+        loss.backward()
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+        cunet_oracle.rmsprop_step(params, grads, sq, 2.5e-4)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    times.sort()
+    return sample_batch / times[len(times) // 2], cores
+
+
+def op_bytes(eng, op, kind):
+    """Algorithmic HBM bytes of one launch (DESIGN.md 'Kernels'): every operand read once, every result written once."""
+    esz = 2 if eng.tdtype.itemsize == 2 else 4
+    N = eng.N
+    src = sum(N * t.res * t.res * t.C * esz for t, _ in op.srcs)
+    out_rows = N * (op.res // 2 if op.pool else op.res) ** 2
+    out = out_rows * op.out.C * (4 if op.out.fp32 else esz)
+    if kind == "fwd":
+        return src + out
+    dy = out if op.out.fp32 else 2 * out          # batch-norm form reads G and T of the output
+    if op.pool:
+        dy += out_rows * op.out.C                 # argmax bytes
+    if kind == "wgrad":
+        return src + dy
+    sched = {o.name: f for o, f in eng.plan.backward_schedule()}
+    gacc = 0
+    for (t, _), (acc, _) in zip(op.srcs, sched[op.name]):
+        b = N * t.res * t.res * t.C * esz
+        gacc += 2 * b if acc else b
+    return src + dy + gacc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cunet8", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--dtype", default="", choices=["", "bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="images in the CPU-baseline sample step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg["batch"] = args.batch
+    if args.dtype:
+        cfg["dtype"] = args.dtype
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if max(args.warmup, 0) < 3:
+        args.warmup = 3
+    workload = "CU-Net-%d order %d loss %d, %d classes, 256x256 -> 64x64 heatmaps, per-GPU batch %d, %s, train step" % (
+        cfg["layer_num"], cfg["order"], cfg["loss_num"], cfg["class_num"], cfg["batch"], cfg["dtype"])
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ips, cores = cpu_reference(cfg, args.cpu_sample, max(1, min(args.steps, 3)))
+        line = dict(impl="reference", metric="images_per_sec", value=ips, unit="images/s", n_gpus=args.gpus,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 * args.cpu_sample / ips,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=workload),
+                    cpu_baseline=dict(value=ips, unit="images/s", cores=cores, kind="port",
+                                      sample="%d-image training step (fwd+MSE+bwd+RMSprop) of the same model, median of %d"
+                                             % (args.cpu_sample, max(1, min(args.steps, 3)))),
+                    e2e=dict(value=ips, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build()
+    from cunet_b200.models.cu_net import create_cu_net
+    from cunet_b200.engine import Trainer
+    from oracle import synthetic                       # synthetic inputs only
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    torch.manual_seed(0)
+    net = create_cu_net(4, 32, 128, cfg["class_num"], cfg["layer_num"], cfg["order"], cfg["loss_num"],
+                        dtype=cfg["dtype"])
+    B = cfg["batch"]
+    tr = Trainer(net, B, lr=2.5e-4, device=dev, process_group=pg, world_size=world, use_graph=not args.no_graph)
+    if world > 1:
+        import torch.distributed as dist
+        dist.broadcast(tr.eng.params, 0)
+    img, hm = synthetic.make_inputs(B, cfg["class_num"], seed=rank)
+    img_h, hm_h = img.pin_memory(), hm.pin_memory()
+    tr.load_batch(img_h, hm_h)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # resident-input steps
+    for _ in range(args.warmup):
+        tr.train_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(lambda: tr.train_step(), args.steps)
+    sampler.stop_flag = True
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step / 1000.0)
+
+    # end-to-end steps: pinned host -> device copies and a device -> host read of the loss every step
+    loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        loss = tr.train_step(img_h, hm_h)
+        loss_host.copy_(loss.view(1), non_blocking=False)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e = world * B / (ms_e2e / 1000.0)
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel, measured live (eager launches bracketed by CUDA events)
+    eng = tr.eng
+    plan = eng.plan
+    pk = peaks()
+    probe_op = max(plan.ops, key=lambda o: (o.cin * o.cout * o.res * o.res, o.index))
+    kinds = ["fwd", "dgrad", "wgrad"]
+    eng.probes = {}
+    evs = {}
+    for k in kinds:
+        prm = eng.call_index[(probe_op.name, k)]
+        evs[k] = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        eng.probes[id(prm)] = evs[k]
+    acc = {k: [] for k in kinds}
+    for _ in range(5):
+        tr._fwd_bwd()
+        eng.optimizer_step()
+        torch.cuda.synchronize()
+        for k in kinds:
+            acc[k].append(evs[k][0].elapsed_time(evs[k][1]))
+    eng.probes = None
+    roofs = {}
+    for k in kinds:
+        t_ms = sorted(acc[k])[len(acc[k]) // 2]
+        by = op_bytes(eng, probe_op, k)
+        flops = 2.0 * eng.N * probe_op.res ** 2 * probe_op.cin * probe_op.cout * probe_op.taps
+        roofs[k] = dict(kernel="conv_%s" % k, op=probe_op.name, us=1000.0 * t_ms, bytes=by,
+                        achieved=by / (t_ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
+                        frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm"], tflops=flops / (t_ms * 1e-3) / 1e12)
+    dom = roofs["dgrad"]
+    train_gflop_img = (3.0 * plan.conv_flops_per_image() - 2.0 * 147 * 128 * 128 * 128) / 1e9
+    tflops = value * train_gflop_img / 1e3
+    line = dict(
+        metric="images_per_sec", value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="bf16" if cfg["dtype"] == "bf16" else "f32(3xtf32)", data="synthetic",
+        config=dict(workload=workload, global_batch=world * B, parallelism="dp%d" % world,
+                    l2="working set (~%.1f GB of activations per step) far exceeds the 126 MB L2; no flush needed"
+                       % (sum(a.numel() * a.element_size() for a in eng.act.values()) / 1e9),
+                    launch="cuda-graph replay" if not args.no_graph else "eager"),
+        e2e=dict(value=e2e, unit="images/s", ms_per_step=ms_e2e,
+                 h2d_bytes_per_step=int(img_h.numel() * 4 + hm_h.numel() * 4), d2h_bytes_per_step=8),
+        gpu_launches=int(eng.launches_per_train_step() * args.steps),
+        roofline=dict(bound="hbm", achieved=dom["achieved"], peak=dom["peak"], unit="GB/s", frac=dom["frac"],
+                      traffic=None, kernel=dom["kernel"], op=dom["op"], us_per_launch=dom["us"],
+                      algorithmic_bytes=dom["bytes"], peak_source=pk["source"],
+                      note="probe launches timed eagerly with CUDA events right after the timed region"),
+        roofline_all=roofs,
+        conv_flops=dict(train_gflop_per_image=train_gflop_img, achieved_tflops=tflops,
+                        frac_of_bf16_sustained=tflops / pk["tf_sust"], peak_tflops=pk["tf_sust"]),
+        clocks=sampler.summary(),
+    )
+    if not args.no_cpu_baseline and world == 1:
+        ips, cores = cpu_reference(cfg, args.cpu_sample, 2)
+        line["cpu_baseline"] = dict(value=ips, unit="images/s", cores=cores, kind="port",
+                                    sample="%d-image training step of the same model on the host, median of 2"
+                                           % args.cpu_sample)
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -189,7 +189,7 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------ launch lists
     def _build_calls(self):
         p, N, lib = self.plan, self.N, L.load()
-        self._keep = []
+        self.call_index = {}      # (op name, "fwd" | "dgrad" | "wgrad") -> parameter struct (bench probes)
 
         def fwd_list(mode):
             calls = []
@@ -227,6 +227,8 @@ class Engine(object):
                 cp.pool_idx = self.pidx[op.out.name].data_ptr() if op.pool else None
                 cp.dtype = self.dtype
                 calls.append((lib.cunet_conv_fwd, cp))
+                if mode:
+                    self.call_index[(op.name, "fwd")] = cp
             return calls
 
         self.fwd_train, self.fwd_eval = fwd_list(1), fwd_list(0)
@@ -284,12 +286,14 @@ class Engine(object):
             dp.dgamma, dp.dbeta = self._gp(op.norm + ".weight"), self._gp(op.norm + ".bias")
             dp.dtype = self.dtype
             calls.append((lib.cunet_conv_dgrad, dp))
+            self.call_index[(op.name, "dgrad")] = dp
             wp = L.ConvWgradParams()
             self._concat(wp.inp, op, 1)
             self._grad_src(wp.dy, op.out, op)
             wp.N, wp.H, wp.W, wp.taps, wp.Cout = N, op.res, op.res, op.taps, op.cout
             wp.dw, wp.nsplit, wp.dtype, wp.dw_cin = self._gp(op.conv + ".weight"), 0, self.dtype, 0
             calls.append((lib.cunet_conv_wgrad, wp))
+            self.call_index[(op.name, "wgrad")] = wp
         # stem backward: parameter-gradient reduction, dy, conv0 wgrad
         for phase in (0, 1):
             sb = L.StemBwdParams()
@@ -319,8 +323,14 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------ execution
     def _run(self, calls):
         st = L.stream_ptr()
+        probes = getattr(self, "probes", None)
         for fn, prm in calls:
+            ev = probes.get(id(prm)) if probes else None
+            if ev is not None:
+                ev[0].record()
             rc = fn(C.byref(prm), st)
+            if ev is not None:
+                ev[1].record()
             if rc != 0:
                 L.check(rc, fn.__name__)
 
@@ -385,20 +395,24 @@ class Engine(object):
 class Trainer(object):
     """Fused training / evaluation steps on one GPU (one process per GPU under data parallelism).
 
-    train_step = H2D(img, heatmap) -> forward -> multi-loss MSE + decode -> backward -> [NCCL allreduce of the
+    train_step = [H2D(img, heatmap)] -> forward -> multi-loss MSE + decode -> backward -> [NCCL allreduce of the
     flat gradient bucket] -> RMSprop -> (weights re-packed at the start of the next step).
     Mirrors train() of the reference (cu-net.py:147-206) with the per-iteration .cpu() metric loops replaced by
-    the fused on-device decode.
+    the fused on-device decode.  With use_graph=True the two launch sequences (forward+loss+backward, optimizer)
+    are captured once into CUDA graphs and replayed; the allreduce runs between them on the same stream.
     """
 
     def __init__(self, net, batch, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, process_group=None,
-                 world_size=1):
+                 world_size=1, use_graph=False):
         self.net = net
         self.eng = net.engine(batch, device)
         self.alpha, self.eps = alpha, eps
         self.set_lr(lr)
         self.pg, self.world = process_group, world_size
         self.eng.grad_scale = 1.0 / world_size
+        self.use_graph = use_graph
+        self._g_fb = self._g_opt = None
+        self.probe = None            # optional (name -> [start_event, end_event]) instrumentation, see bench.py
 
     def set_lr(self, lr):
         self.eng.lr.fill_(lr)
@@ -408,17 +422,45 @@ class Trainer(object):
         self.eng.img.copy_(img, non_blocking=True)
         self.eng.target.copy_(heatmap, non_blocking=True)
 
+    def _fwd_bwd(self):
+        e = self.eng
+        e.forward(train=True)
+        e.loss_and_decode(with_grad=True)
+        e.backward()
+
+    def _capture(self):
+        # warm-up on a side stream (sets kernel attributes, allocates nothing afterwards), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._fwd_bwd()
+            self.eng.optimizer_step(self.alpha, self.eps)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fb):
+            self._fwd_bwd()
+        self._g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_opt):
+            self.eng.optimizer_step(self.alpha, self.eps)
+
     def train_step(self, img=None, heatmap=None):
         e = self.eng
         if img is not None:
             self.load_batch(img, heatmap)
-        e.forward(train=True)
-        e.loss_and_decode(with_grad=True)
-        e.backward()
+        if self.use_graph:
+            if self._g_fb is None:
+                self._capture()
+            self._g_fb.replay()
+        else:
+            self._fwd_bwd()
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(e.grads, group=self.pg)       # gradients were pre-scaled by 1/world (sum == mean)
-        e.optimizer_step(self.alpha, self.eps)
+        if self.use_graph:
+            self._g_opt.replay()
+        else:
+            e.optimizer_step(self.alpha, self.eps)
         return e.loss_value()
 
     def eval_step(self, img=None, heatmap=None):
