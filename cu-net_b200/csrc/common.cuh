@@ -268,6 +268,22 @@ template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float* f)
   f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xFFFF0000u);
   f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xFFFF0000u);
 }
+// raw (still packed) 4-element load, for prefetching many rows without spending fp32 registers on them
+template <typename T> struct Raw4;
+template <> struct Raw4<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void get(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+};
+template <> struct Raw4<bf16> {
+  uint2 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void get(float* f) const {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xFFFF0000u);
+  }
+};
+
 // store 4 elements; returns the values as stored (after rounding to T) in f
 template <typename T> __device__ __forceinline__ void store4(T* p, float* f);
 template <> __device__ __forceinline__ void store4<float>(float* p, float* f) {
@@ -290,26 +306,52 @@ struct PixGeom {
   int N, H, W;      // full-resolution dims of this op
   int M;            // N*H*W
 };
+// 32-bit index math only (64-bit division is ~100 instructions on the GPU); shifts when W, H are powers of two.
+__device__ __forceinline__ void pix_split(int m, int H, int W, int& n, int& h, int& w) {
+  if (((W & (W - 1)) | (H & (H - 1))) == 0) {
+    const int lw = __ffs(W) - 1, lh = __ffs(H) - 1;
+    w = m & (W - 1);
+    const int t = m >> lw;
+    h = t & (H - 1);
+    n = t >> lh;
+  } else {
+    w = m % W;
+    const int t = m / W;
+    h = t % H;
+    n = t / H;
+  }
+}
 __device__ __forceinline__ bool tile_row_pixel(const PixGeom& g, int tile, int r, int grouped, int& n, int& h, int& w) {
   if (!grouped) {
-    long m = (long)tile * 128 + r;
+    const int m = tile * 128 + r;
     if (m >= g.M) return false;
-    w = (int)(m % g.W);
-    long t = m / g.W;
-    h = (int)(t % g.H);
-    n = (int)(t / g.H);
+    pix_split(m, g.H, g.W, n, h, w);
     return true;
   } else {
-    long win = (long)tile * 32 + (r >> 2);
-    int Wh = g.W >> 1, Hh = g.H >> 1;
-    if (win >= (long)g.N * Hh * Wh) return false;
-    int ww = (int)(win % Wh);
-    long t = win / Wh;
-    int hh = (int)(t % Hh);
-    n = (int)(t / Hh);
+    const int win = tile * 32 + (r >> 2);
+    const int Wh = g.W >> 1, Hh = g.H >> 1;
+    if (win >= g.N * Hh * Wh) return false;
+    int hh, ww;
+    pix_split(win, Hh, Wh, n, hh, ww);
     h = hh * 2 + ((r >> 1) & 1);
     w = ww * 2 + (r & 1);
     return true;
+  }
+}
+
+// per-CTA table of the tile's 128 rows (computed once by 128 threads, read by loaders and epilogues)
+struct TileRowTable {
+  int rd[128];  // full-resolution row index or -1
+  int ru[128];  // half-resolution row index
+  int hw[128];  // (h << 16) | w
+};
+__device__ __forceinline__ void tile_rows_init(TileRowTable* t, const PixGeom& g, int tile, int grouped, int tid) {
+  if (tid < 128) {
+    int n = 0, h = 0, w = 0;
+    const bool valid = tile_row_pixel(g, tile, tid, grouped, n, h, w);
+    t->rd[tid] = valid ? (n * g.H + h) * g.W + w : -1;
+    t->ru[tid] = valid ? (n * (g.H >> 1) + (h >> 1)) * (g.W >> 1) + (w >> 1) : 0;
+    t->hw[tid] = (h << 16) | w;
   }
 }
 

@@ -28,10 +28,14 @@ struct DgSmemTail {
   uint32_t tmem_base;
   BnSmem bn;
   GradSmem gc;
+  TileRowTable rows;
 };
 
+#ifndef DG_MIN_CTAS
+#define DG_MIN_CTAS StageGeom<T>::MIN_CTAS
+#endif
 template <typename T>
-__global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad_kernel(const __grid_constant__ cunet_conv_dgrad_params p) {
+__global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(const __grid_constant__ cunet_conv_dgrad_params p) {
   using E = Elem<T>;
   using SG = StageGeom<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -59,23 +63,26 @@ __global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad
   if (warp == 9) tmem_alloc(&tail->tmem_base, 128);
   compute_bn_coefs(p.in, &tail->bn, ((Cin + 127) / 128) * 128, tid, DG_THREADS);
   compute_grad_coefs(p.dy, &tail->gc, tid, DG_THREADS);
+  PixGeom geom;
+  geom.N = p.N; geom.H = p.H; geom.W = p.W; geom.M = p.N * p.H * p.W;
+  tile_rows_init(&tail->rows, geom, tile, grouped, tid);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
 
-  PixGeom geom;
-  geom.N = p.N; geom.H = p.H; geom.W = p.W; geom.M = p.N * p.H * p.W;
-
   if (warp < 8) {
     // ============================================================== A loaders (gradient operand)
     const int c = tid & 7;
-    int rn[4], rh[4], rw[4];
-    uint32_t rvalid = 0;
+    RowCtx rc;
+    uint32_t soff[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int r = (tid >> 3) + 32 * q;
-      if (tile_row_pixel(geom, tile, r, grouped, rn[q], rh[q], rw[q])) rvalid |= 1u << q;
+      rc.rd[q] = tail->rows.rd[r];
+      rc.ru[q] = tail->rows.ru[r];
+      rc.hw[q] = tail->rows.hw[r];
+      soff[q] = tile_off(r, c);
     }
     GradRaw<T> cur[4], nxt[4];
     uint32_t cmask = 0, nmask = 0;
@@ -92,12 +99,10 @@ __global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad
         dy = tap / 3 - 1;
         dx = tap - (tap / 3) * 3 - 1;
       }
+      // out(px) reads in(px + off)  =>  in(px) receives from out(px - off)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (!((rvalid >> q) & 1)) continue;
-        // out(px) reads in(px + off)  =>  in(px) receives from out(px - off)
-        if (grad_issue<T>(p.dy, p.H, p.W, co, rn[q], rh[q] - dy, rw[q] - dx, dst[q])) mask |= 1u << q;
-      }
+      for (int q = 0; q < 4; ++q)
+        if (grad_load<T>(p.dy, rc, q, p.H, p.W, co, -dy, -dx, dst[q])) mask |= 1u << q;
     };
 
     issue(0, cur, cmask, cco);
@@ -105,15 +110,16 @@ __global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad
       const int s = it % DG_STAGES;
       const uint32_t ph = (it / DG_STAGES) & 1;
       if (it + 1 < nsteps) issue(it + 1, nxt, nmask, nco);
+      GradCoef<T> cf;
+      cf.load(&tail->gc, cco & 127);
       mbar_wait(&tail->empty[s], ph ^ 1);
       const uint32_t abase = smem_u32(smem + s * SG::BYTES);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int r = (tid >> 3) + 32 * q;
         uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-        if ((cmask >> q) & 1) o = grad_transform<T>(p.dy, &tail->gc, cco, cur[q], lo);
-        sts128(abase + tile_off(r, c), o);
-        if (SG::SPLIT) sts128(abase + SG::A_LO + tile_off(r, c), lo);
+        if ((cmask >> q) & 1) o = cf.apply(p.dy, cur[q], lo);
+        sts128(abase + soff[q], o);
+        if (SG::SPLIT) sts128(abase + SG::A_LO + soff[q], lo);
       }
       fence_proxy_async();
       __syncwarp();
@@ -165,6 +171,25 @@ __global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad
   constexpr int LD_EP = 132;
   float* ep = reinterpret_cast<float*>(smem);
   float* red = reinterpret_cast<float*>(smem + 128 * LD_EP * 4);  // [256][16] partial sums
+
+  // thread -> channel quad (32 quads per chunk) x 8 row groups.  Each quad lies inside one segment.
+  float a_db[4] = {0, 0, 0, 0}, a_dg[4] = {0, 0, 0, 0}, a_g[4] = {0, 0, 0, 0}, a_gt[4] = {0, 0, 0, 0};
+  const int quad = tid & 31;
+  const int rg = tid >> 5;  // 0..7 for the epilogue warps
+  const int k0 = chunk * 128 + quad * 4;
+  bool active = warp < 8 && k0 < Cin;
+  int sidx = 0;
+  if (active) {
+    while (k0 >= tail->bn.seg_start[sidx + 1]) ++sidx;
+    if (p.gacc[sidx].G == nullptr) active = false;
+  }
+  const cunet_seg& sg = p.in.seg[sidx];
+  const cunet_gacc& ga = p.gacc[sidx];
+  const int cl = k0 - tail->bn.seg_start[sidx];
+  const T* src = reinterpret_cast<const T*>(sg.ptr);
+  T* G = reinterpret_cast<T*>(ga.G);
+  const int nrow_it = (active && sg.up) ? 4 : 16;  // up: 4 windows per thread, else 16 rows per thread
+
   if (warp < 8) {
     mbar_wait(&tail->accum, 0);
     tc_fence_after();
@@ -182,20 +207,7 @@ __global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad
   }
   __syncthreads();
 
-  // thread -> channel quad (32 quads per chunk), 8 row groups.  Each quad lies inside one segment.
-  float a_db[4] = {0, 0, 0, 0}, a_dg[4] = {0, 0, 0, 0}, a_g[4] = {0, 0, 0, 0}, a_gt[4] = {0, 0, 0, 0};
-  const int quad = tid & 31;
-  const int k0 = chunk * 128 + quad * 4;
-  bool active = warp < 8 && k0 < Cin;
-  int sidx = 0;
   if (active) {
-    while (k0 >= tail->bn.seg_start[sidx + 1]) ++sidx;
-    if (p.gacc[sidx].G == nullptr) active = false;
-  }
-  if (active) {
-    const cunet_seg& sg = p.in.seg[sidx];
-    const cunet_gacc& ga = p.gacc[sidx];
-    const int cl = k0 - tail->bn.seg_start[sidx];
     float sc[4], sh[4], mu[4], is[4], gm[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -205,77 +217,55 @@ __global__ void __launch_bounds__(DG_THREADS, StageGeom<T>::MIN_CTAS) conv_dgrad
       is[e] = tail->bn.istd[k0 + e];
       gm[e] = p.in.gamma[k0 + e];
     }
-    const T* src = reinterpret_cast<const T*>(sg.ptr);
-    T* G = reinterpret_cast<T*>(ga.G);
-    const int rg = tid >> 5;  // 0..7
-    if (!sg.up) {
-      for (int r = rg; r < 128; r += 8) {
-        int n, h, w;
-        if (!tile_row_pixel(geom, tile, r, grouped, n, h, w)) continue;
-        const long row = ((long)n * p.H + h) * p.W + w;
+    // one row (or one 2x2 window of an upsampled source) per iteration; kept deliberately light on registers:
+    // at 2 CTAs / SM a deeper register prefetch spills and measured slower ("dgrad epilogue")
+    for (int j = 0; j < nrow_it; ++j) {
+      const int r = sg.up ? 4 * (rg + 8 * j) : rg + 8 * j;
+      const int rd = tail->rows.rd[r];
+      if (rd < 0) continue;
+      const long row = sg.up ? tail->rows.ru[r] : rd;
+      float gv[4] = {0, 0, 0, 0}, xv[4];
+      load4<T>(src + row * sg.ld + cl, xv);
+      if (!sg.up) {
         const float4 a = *reinterpret_cast<const float4*>(ep + r * LD_EP + quad * 4);
         const float av[4] = {a.x, a.y, a.z, a.w};
-        float x[4], gv[4];
-        load4<T>(src + row * sg.ld + cl, x);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float z = fmaf(x[e], sc[e], sh[e]);
+          const float z = fmaf(xv[e], sc[e], sh[e]);
           const float dz = z > 0.f ? av[e] : 0.f;
           a_db[e] += dz;
-          a_dg[e] += dz * (x[e] - mu[e]) * is[e];
+          a_dg[e] += dz * (xv[e] - mu[e]) * is[e];
           gv[e] = gm[e] * dz;
         }
-        T* gp = G + row * ga.ld + cl;
-        if (ga.accumulate) {
-          float old[4];
-          load4<T>(gp, old);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) gv[e] += old[e];
-        }
-        store4<T>(gp, gv);  // gv <- values as stored
-        if (ga.gstats) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            a_g[e] += gv[e];
-            a_gt[e] += gv[e] * (x[e] - mu[e]) * is[e];
-          }
-        }
-      }
-    } else {
-      // upsampled source: rows 4q..4q+3 of the (grouped) tile are the four children of one low-res pixel
-      for (int q = rg; q < 32; q += 8) {
-        int n, h, w;
-        if (!tile_row_pixel(geom, tile, 4 * q, 1, n, h, w)) continue;
-        const long row = ((long)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-        float x[4], gv[4] = {0, 0, 0, 0};
-        load4<T>(src + row * sg.ld + cl, x);
+      } else {
+        // upsampled source: tile rows r..r+3 are the four children of one low-resolution pixel
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const float4 a = *reinterpret_cast<const float4*>(ep + (4 * q + ch) * LD_EP + quad * 4);
+          const float4 a = *reinterpret_cast<const float4*>(ep + (r + ch) * LD_EP + quad * 4);
           const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float z = fmaf(x[e], sc[e], sh[e]);
+            const float z = fmaf(xv[e], sc[e], sh[e]);
             const float dz = z > 0.f ? av[e] : 0.f;
             a_db[e] += dz;
-            a_dg[e] += dz * (x[e] - mu[e]) * is[e];
+            a_dg[e] += dz * (xv[e] - mu[e]) * is[e];
             gv[e] += gm[e] * dz;
           }
         }
-        T* gp = G + row * ga.ld + cl;
-        if (ga.accumulate) {
-          float old[4];
-          load4<T>(gp, old);
+      }
+      T* gp = G + row * ga.ld + cl;
+      if (ga.accumulate) {
+        float ov[4];
+        load4<T>(gp, ov);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) gv[e] += old[e];
-        }
-        store4<T>(gp, gv);  // gv <- values as stored
-        if (ga.gstats) {
+        for (int e = 0; e < 4; ++e) gv[e] += ov[e];
+      }
+      store4<T>(gp, gv);  // gv <- values as stored
+      if (ga.gstats) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            a_g[e] += gv[e];
-            a_gt[e] += gv[e] * (x[e] - mu[e]) * is[e];
-          }
+        for (int e = 0; e < 4; ++e) {
+          a_g[e] += gv[e];
+          a_gt[e] += gv[e] * (xv[e] - mu[e]) * is[e];
         }
       }
     }

@@ -28,6 +28,7 @@ struct FwdSmemTail {
   uint64_t accum;
   uint32_t tmem_base;
   BnSmem bn;
+  TileRowTable rows;
 };
 
 template <typename T>
@@ -58,23 +59,26 @@ __global__ void __launch_bounds__(FWD_THREADS, StageGeom<T>::MIN_CTAS) conv_fwd_
   }
   if (warp == 9) tmem_alloc(&tail->tmem_base, tmem_cols);
   compute_bn_coefs(p.in, &tail->bn, nkb * E::KBE, tid, FWD_THREADS);
+  PixGeom geom;
+  geom.N = p.N; geom.H = p.H; geom.W = p.W; geom.M = p.N * p.H * p.W;
+  tile_rows_init(&tail->rows, geom, tile, grouped, tid);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
 
-  PixGeom geom;
-  geom.N = p.N; geom.H = p.H; geom.W = p.W; geom.M = p.N * p.H * p.W;
-
   if (warp < 8) {
     // ============================================================== A loaders
     const int c = tid & 7;
-    int rn[4], rh[4], rw[4];
-    uint32_t rvalid = 0;
+    RowCtx rc;
+    uint32_t soff[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int r = (tid >> 3) + 32 * q;
-      if (tile_row_pixel(geom, tile, r, grouped, rn[q], rh[q], rw[q])) rvalid |= 1u << q;
+      rc.rd[q] = tail->rows.rd[r];
+      rc.ru[q] = tail->rows.ru[r];
+      rc.hw[q] = tail->rows.hw[r];
+      soff[q] = tile_off(r, c);
     }
     uint4 cur[4], nxt[4];
     uint32_t cmask = 0, nmask = 0;
@@ -82,17 +86,15 @@ __global__ void __launch_bounds__(FWD_THREADS, StageGeom<T>::MIN_CTAS) conv_fwd_
     auto issue = [&](int it, uint4* dst, uint32_t& mask) {
       mask = 0;
       const int tap = it / nkb, kb = it - tap * nkb;
-      const int ch = kb * E::KBE + c * E::EPC;
       int dy = 0, dx = 0;
       if (p.taps == 9) {
         dy = tap / 3 - 1;
         dx = tap - (tap / 3) * 3 - 1;
       }
+      const ActStep st = act_step<T>(p.in, &tail->bn, kb * E::KBE + c * E::EPC);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (!((rvalid >> q) & 1)) continue;
-        if (act_issue<T>(p.in, &tail->bn, p.H, p.W, ch, rn[q], rh[q], rw[q], dy, dx, dst[q])) mask |= 1u << q;
-      }
+      for (int q = 0; q < 4; ++q)
+        if (act_load(st, rc, q, p.H, p.W, dy, dx, dst[q])) mask |= 1u << q;
     };
 
     issue(0, cur, cmask);
@@ -100,17 +102,16 @@ __global__ void __launch_bounds__(FWD_THREADS, StageGeom<T>::MIN_CTAS) conv_fwd_
       const int s = it % FWD_STAGES;
       const uint32_t ph = (it / FWD_STAGES) & 1;
       if (it + 1 < nsteps) issue(it + 1, nxt, nmask);
+      ActCoef<T> cf;
+      cf.load(&tail->bn, (it % nkb) * E::KBE + c * E::EPC);
       mbar_wait(&tail->empty[s], ph ^ 1);
-      const int kb = it % nkb;
-      const int ch = kb * E::KBE + c * E::EPC;
       const uint32_t abase = smem_u32(smem + s * SG::BYTES);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int r = (tid >> 3) + 32 * q;
         uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-        if ((cmask >> q) & 1) o = act_transform<T>(&tail->bn, ch, cur[q], lo);
-        sts128(abase + tile_off(r, c), o);
-        if (SG::SPLIT) sts128(abase + SG::A_LO + tile_off(r, c), lo);
+        if ((cmask >> q) & 1) o = cf.apply(cur[q], lo);
+        sts128(abase + soff[q], o);
+        if (SG::SPLIT) sts128(abase + SG::A_LO + soff[q], lo);
       }
       fence_proxy_async();
       __syncwarp();

@@ -83,6 +83,28 @@ __global__ void __launch_bounds__(WG_THREADS, StageGeom<T>::MIN_CTAS) conv_wgrad
     const int acc = tid % G::CPR, ar0 = tid / G::CPR;  // activation: fixed chunk column, 4 rows
     const int ach = chunk * 128 + acc * E::EPC;
     const int cprb = npad / E::EPC;                    // gradient chunks per pixel row
+    const ActStep ast = act_step<T>(p.in, &tail->bn, ach);
+    ActCoef<T> acf;
+    acf.load(&tail->bn, ach);
+    PixDiv pd;
+    pd.init(p.H, p.W);
+    // gradient chunks of this thread: idx = tid + 256*q -> (row, chunk column); fixed across stages
+    int grow[4], gco[4];
+    uint32_t goff[4], aoff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + 256 * q;
+      grow[q] = -1;
+      gco[q] = 0;
+      goff[q] = 0;
+      if (idx < G::R * cprb) {
+        const int r = idx / cprb, cc = idx - r * cprb;
+        grow[q] = r;
+        gco[q] = cc * E::EPC;
+        goff[q] = (cc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, cc & 7);
+      }
+      aoff[q] = (acc >> 3) * G::SUB_BYTES + tile_off_mn<T>(ar0 + G::RPP * q, acc & 7);
+    }
     uint4 araw[4];
     GradRaw<T> graw[4];
 
@@ -91,55 +113,46 @@ __global__ void __launch_bounds__(WG_THREADS, StageGeom<T>::MIN_CTAS) conv_wgrad
       const uint32_t ph = (it / WG_STAGES) & 1;
       const long m0 = (long)(st0 + it) * G::R;
       uint32_t amask = 0, gmask = 0;
-      int gco[4];
+      RowCtx arc, grc;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const long m = m0 + ar0 + G::RPP * q;
-        if (m < M) {
-          const int w = (int)(m % p.W);
-          const long t = m / p.W;
-          const int h = (int)(t % p.H), n = (int)(t / p.H);
-          if (act_issue<T>(p.in, &tail->bn, p.H, p.W, ach, n, h, w, dy, dx, araw[q])) amask |= 1u << q;
-        }
+        int n = 0, h = 0, w = 0;
+        const bool valid = m < M;
+        if (valid) pd.split((int)m, n, h, w);
+        rowctx_set(arc, q, valid, n, h, w, p.H, p.W);
+        if (act_load(ast, arc, q, p.H, p.W, dy, dx, araw[q])) amask |= 1u << q;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int idx = tid + 256 * q;
-        gco[q] = 0;
-        if (idx < G::R * cprb) {
-          const int r = idx / cprb, cc = idx - r * cprb;
-          gco[q] = cc * E::EPC;
-          const long m = m0 + r;
-          if (m < M) {
-            const int w = (int)(m % p.W);
-            const long t = m / p.W;
-            const int h = (int)(t % p.H), n = (int)(t / p.H);
-            if (grad_issue<T>(p.dy, p.H, p.W, gco[q], n, h, w, graw[q])) gmask |= 1u << q;
-          }
-        }
+        const long m = m0 + grow[q];
+        int n = 0, h = 0, w = 0;
+        const bool valid = grow[q] >= 0 && m < M;
+        if (valid) pd.split((int)m, n, h, w);
+        rowctx_set(grc, q, valid, n, h, w, p.H, p.W);
+        if (grad_load<T>(p.dy, grc, q, p.H, p.W, gco[q], 0, 0, graw[q])) gmask |= 1u << q;
       }
       mbar_wait(&tail->empty[s], ph ^ 1);
       const uint32_t abase = smem_u32(smem + s * SG::BYTES);
       const uint32_t bbase = abase + SG::B_OFF;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int r = ar0 + G::RPP * q;
         uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-        if ((amask >> q) & 1) o = act_transform<T>(&tail->bn, ach, araw[q], lo);
-        const uint32_t off = (acc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, acc & 7);
-        sts128(abase + off, o);
-        if (SG::SPLIT) sts128(abase + SG::A_LO + off, lo);
+        if ((amask >> q) & 1) o = acf.apply(araw[q], lo);
+        sts128(abase + aoff[q], o);
+        if (SG::SPLIT) sts128(abase + SG::A_LO + aoff[q], lo);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int idx = tid + 256 * q;
-        if (idx < G::R * cprb) {
-          const int r = idx / cprb, cc = idx - r * cprb;
+        if (grow[q] >= 0) {
           uint4 o = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-          if ((gmask >> q) & 1) o = grad_transform<T>(p.dy, &tail->gc, gco[q], graw[q], lo);
-          const uint32_t off = (cc >> 3) * G::SUB_BYTES + tile_off_mn<T>(r, cc & 7);
-          sts128(bbase + off, o);
-          if (SG::SPLIT) sts128(bbase + 16384 + off, lo);
+          if ((gmask >> q) & 1) {
+            GradCoef<T> gcf;
+            gcf.load(&tail->gc, gco[q] & 127);
+            o = gcf.apply(p.dy, graw[q], lo);
+          }
+          sts128(bbase + goff[q], o);
+          if (SG::SPLIT) sts128(bbase + 16384 + goff[q], lo);
         }
       }
       fence_proxy_async();
@@ -224,7 +237,17 @@ extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) 
   const int npad = ((p->dy.C + kbe - 1) / kbe) * kbe;  // whole MN groups of the gradient operand
   const int ny = ((cin + 127) / 128) * p->taps;
   const int total_steps = (int)((M + R - 1) / R);
-  int nsplit = p->nsplit > 0 ? p->nsplit : (296 + ny - 1) / ny;
+  // one wave: as many CTAs as are co-resident (launch bounds: 2 CTAs / SM for bf16, 1 for the fp32 split
+  // mode; ncu launch__occupancy_limit_* confirms), never a partial second wave
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int slots = sms * (p->dtype == CUNET_BF16 ? StageGeom<bf16>::MIN_CTAS : StageGeom<float>::MIN_CTAS);
+  int nsplit = p->nsplit > 0 ? p->nsplit : slots / ny;
   if (nsplit > total_steps) nsplit = total_steps;
   if (nsplit < 1) nsplit = 1;
   dim3 grid((unsigned)nsplit, (unsigned)ny);

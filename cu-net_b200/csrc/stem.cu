@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const cunet_stem_bwd_para
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int c = quad * 4 + e;
-      dxv[e] = gc.istd[c] * (g[e] - gc.c1[c] - (xv[e] - gc.mu[c]) * gc.c2[c]);
+      dxv[e] = fmaf(gc.a[c], g[e], fmaf(gc.b[c], xv[e] - gc.mu[c], gc.d[c]));
     }
     float v[4][4], z[4][4];
     int am[4] = {0, 0, 0, 0};
