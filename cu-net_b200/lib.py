@@ -84,6 +84,11 @@ class MseParams(C.Structure):
                 ("dtype", C.c_int)]
 
 
+class QuantDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("saved", C.c_void_p), ("grad", C.c_void_p),
+                ("Cout", C.c_int), ("Cin", C.c_int), ("taps", C.c_int), ("first_block", C.c_int)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [("w", C.c_void_p), ("fwd", C.c_void_p), ("dgrad", C.c_void_p),
                 ("Cout", C.c_int), ("Cin", C.c_int), ("taps", C.c_int), ("CoutPad", C.c_int)]
@@ -117,6 +122,8 @@ EXPORTS = [
     "cunet_conv_fwd", "cunet_conv_dgrad", "cunet_conv_wgrad", "cunet_pack_weights", "cunet_pack_fwd_bytes",
     "cunet_pack_dgrad_bytes", "cunet_stem_im2col", "cunet_stem_pool_fwd", "cunet_stem_bwd", "cunet_mse_decode",
     "cunet_decode_finalize", "cunet_bn_running_update", "cunet_rmsprop_step",
+    "cunet_quant_forward", "cunet_quant_restore", "cunet_quant_grad", "cunet_quant_input_fwd",
+    "cunet_quant_input_bwd",
 ]
 
 

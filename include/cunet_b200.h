@@ -216,6 +216,37 @@ int cunet_bn_running_update(const cunet_bn_update_desc* descs_dev, int ndesc, vo
 int cunet_rmsprop_step(float* params, const float* grads, float* square_avg, long n, const float* lr_dev,
                        float alpha, float eps, void* stream);
 
+/* ---- weight / activation / gradient quantizers ---------------------------------------------------------
+ * QuanOp (utils/quantize.py:77-175) and BinOp (models/cu_net_prev_version.py:17-92) as multi-tensor launches:
+ * one thread block per filter (output channel) of every target conv, all targets in one launch.
+ *   forward (mode 0, QuanOp.quantization, quantize.py:104-149):
+ *       w -= mean over Cin;  w = clamp(w, +-(1 - 2^-(bits_g-1)));  saved = round(w*2^(bits_g-1))/2^(bits_g-1);
+ *       bits_w == 1: w = sign(w) [the scale is dropped by the fall-through at quantize.py:135,148-149]
+ *       bits_w == 2: w = +1 if w > d, -1 if w < -d, else 0,  d = 0.7 * mean_filter |w|
+ *       else       : w = round(clamp(w)*2^(bits_w-1))/2^(bits_w-1)
+ *   forward (mode 1, BinOp.binarization, cu_net_prev_version.py:43-72):
+ *       w -= mean over Cin;  w = clamp(w, +-1);  saved = w;  w = sign(w) * mean_filter |w|
+ *   restore: w = saved                                         (quantize.py:151-153, cu_net_prev_version.py:74-76)
+ *   grad (quantize.py:156-175, cu_net_prev_version.py:78-92), w = restored weights:
+ *       bits_w == 1 or BinOp: g = (m*g + sign(w)*mean_filter(sign(w)*g)) * (1 - 1/Cin) * n,
+ *                            m = mean_filter|w| where |w| <= 1 else 0  [QuanOp: m rounded to the bits_g grid]
+ *       QuanOp: g = round(clamp(g)*2^(bits_g-1))/2^(bits_g-1) afterwards (and only that when bits_w != 1) */
+typedef struct {
+  float* w;        /* [Cout][Cin][taps] fp32 parameter (modified in place) */
+  float* saved;    /* same shape: full-precision copy */
+  float* grad;     /* same shape, or NULL */
+  int Cout, Cin, taps;
+  int first_block; /* index of this tensor's first filter in the launch grid */
+} cunet_quant_desc;
+int cunet_quant_forward(const cunet_quant_desc* descs_dev, int ndesc, int nblocks, int mode, int bits_w, int bits_g,
+                        void* stream);
+int cunet_quant_restore(const cunet_quant_desc* descs_dev, int ndesc, int nblocks, void* stream);
+int cunet_quant_grad(const cunet_quant_desc* descs_dev, int ndesc, int nblocks, int mode, int bits_w, int bits_g,
+                     void* stream);
+/* QuanInput (utils/quantize.py:47-63): y = Q(C(x, bits), bits);  backward: dx = dy where |x| < 1 else 0 */
+int cunet_quant_input_fwd(const float* x, float* y, long n, int bits, void* stream);
+int cunet_quant_input_bwd(const float* x, const float* dy, float* dx, long n, void* stream);
+
 /* Weight packing: reference-layout fp32 master weights -> tensor-core operand images.
  * One descriptor per conv; all descriptors processed by one launch.
  *   fwd image  : [tap][kb][CoutPad rows][128 B]  K = input channel  (B operand of the forward GEMM)
