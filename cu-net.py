@@ -1,0 +1,167 @@
+#!/usr/bin/env python
+"""Train / evaluate a CU-Net on the B200-native path -- drop-in for the reference's ``cu-net.py``.
+
+Same flags as the reference (options/base_options.py, options/train_options.py): --layer_num --order --class_num
+--loss_num --lr --bs --nEpochs --gpu_id --is_train --exp_dir --exp_id --resume_prefix --bits_w --bits_g ...
+Deliberate deviations (documented in DESIGN.md):
+  * boolean flags parse "false"/"0"/"no" as False (the reference's ``type=bool`` makes ``--is_train false`` True);
+  * --loss_num defaults to --layer_num when the reference default (16) would violate loss_num <= layer_num;
+  * multi-GPU is one process per GPU (torchrun) with one NCCL allreduce per step instead of nn.DataParallel
+    (cu-net.py:59); --gpu_id selects the device of a single process;
+  * the datasets (MPII / FACE image folders) are not shipped: --data synthetic (default) draws the seeded
+    synthetic batches of SURVEY.md section 8(d); a torch DataLoader yielding (img, heatmap) can be plugged in
+    through run(..., loader=...).
+The step itself is train() / validate() of cu-net.py:147-278: net(img), multi-loss MSE, backward, RMSprop, with the
+per-iteration .cpu() metric loops replaced by the fused on-device landmark decode (--fused, default) or, with
+--no-fused, literally the reference's sequence through the module API (loss.backward(); optimizer.step()).
+"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def str2bool(v):
+    return str(v).lower() not in ("false", "0", "no", "off", "")
+
+
+def parse(argv=None):
+    ap = argparse.ArgumentParser()
+    # options/base_options.py:13-35
+    ap.add_argument("--data_dir", type=str, default="./dataset")
+    ap.add_argument("--exp_dir", type=str, default="./exp")
+    ap.add_argument("--exp_id", type=str, default="")
+    ap.add_argument("--gpu_id", type=str, default="0")
+    ap.add_argument("--nThreads", type=int, default=4)
+    ap.add_argument("--is_train", type=str2bool, default=True)
+    ap.add_argument("--dataset", type=str, default="mpii")
+    # options/train_options.py:7-38
+    ap.add_argument("--layer_num", type=int, default=2)
+    ap.add_argument("--order", type=int, default=1)
+    ap.add_argument("--class_num", type=int, default=16)
+    ap.add_argument("--loss_num", type=int, default=16)
+    ap.add_argument("--lr", type=float, default=2.5e-4)
+    ap.add_argument("--bs", type=int, default=24)
+    ap.add_argument("--adjust_lr", type=str2bool, default=False)
+    ap.add_argument("--resume_prefix", type=str, default="")
+    ap.add_argument("--nEpochs", type=int, default=200)
+    ap.add_argument("--print_freq", type=int, default=10)
+    ap.add_argument("--bits_w", type=int, default=1)
+    ap.add_argument("--bits_i", type=int, default=8)
+    ap.add_argument("--bits_g", type=int, default=8)
+    # B200 path
+    ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--quant", choices=["none", "bin", "quan"], default="none",
+                    help="bin: BinOp protocol (cu-net-prev-version-bin.py); quan: QuanOp (…-wig.py)")
+    ap.add_argument("--data", choices=["synthetic"], default="synthetic")
+    ap.add_argument("--iters_per_epoch", type=int, default=20)
+    ap.add_argument("--fused", dest="fused", action="store_true", default=True)
+    ap.add_argument("--no-fused", dest="fused", action="store_false")
+    opt = ap.parse_args(argv)
+    if opt.loss_num > opt.layer_num:
+        opt.loss_num = opt.layer_num
+    return opt
+
+
+def adjust_lr(opt, epoch):
+    """utils/util.py:106-119: x0.2 at epoch 101, x0.5 at 141 and 161."""
+    if epoch == 101:
+        opt.lr *= 0.2
+    elif epoch in (141, 161):
+        opt.lr *= 0.5
+    return opt.lr
+
+
+def run(opt, loader=None):
+    import torch
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build()
+    from cunet_b200.models.cu_net import create_cu_net
+    from cunet_b200.engine import Trainer
+    from cunet_b200.utils.quantize import BinOp, QuanOp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", opt.gpu_id.split(",")[0]))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    torch.manual_seed(0)
+    net = create_cu_net(neck_size=4, growth_rate=32, init_chan_num=128, class_num=opt.class_num,
+                        layer_num=opt.layer_num, order=opt.order, loss_num=opt.loss_num, dtype=opt.dtype)
+    bs = max(1, opt.bs // world)              # the reference's DataParallel splits --bs over the GPUs (cu-net.py:59,84)
+    eng = net.engine(bs, dev)
+    quant = None
+    if opt.quant == "bin":
+        quant = BinOp(net)
+    elif opt.quant == "quan":
+        quant = QuanOp(net, bits_w=opt.bits_w, bits_g=opt.bits_g)
+    tr = Trainer(net, bs, lr=opt.lr, device=dev, process_group=pg, world_size=world, quant=quant)
+    if world > 1:
+        import torch.distributed as dist
+        dist.broadcast(eng.params, 0)
+    if loader is None:
+        sys.path.insert(0, ROOT)
+        from oracle import synthetic             # synthetic batches only
+
+        def loader_fn(epoch):
+            for it in range(opt.iters_per_epoch):
+                yield synthetic.make_inputs(bs, opt.class_num, seed=1000 * epoch + it * world + rank)
+    else:
+        def loader_fn(epoch):
+            return iter(loader)
+    history = []
+    if not opt.is_train:
+        net.eval()
+        losses = []
+        if quant is not None:
+            (quant.binarization if opt.quant == "bin" else quant.quantization)()
+        for img, hm in loader_fn(0):
+            loss, preds = tr.eval_step(img.to(dev), hm.to(dev))
+            losses.append(float(loss))
+        if quant is not None:
+            quant.restore()
+        if rank == 0:
+            print("val loss %.6f" % (sum(losses) / max(1, len(losses))))
+        return losses
+    net.train()
+    opt_torch = None
+    if not opt.fused:
+        opt_torch = torch.optim.RMSprop(net.parameters(), lr=opt.lr, alpha=0.99, eps=1e-8, momentum=0, weight_decay=0)
+    for epoch in range(opt.nEpochs):
+        if opt.adjust_lr:
+            tr.set_lr(adjust_lr(opt, epoch))
+        t0, n_img, last = time.time(), 0, 0.0
+        for i, (img, hm) in enumerate(loader_fn(epoch)):
+            if opt.fused:
+                last = float(tr.train_step(img.to(dev, non_blocking=True), hm.to(dev, non_blocking=True)))
+            else:   # the reference's literal step through the module API (cu-net.py:171-183)
+                out = net(img.to(dev))
+                loss = 0
+                for o in out:
+                    d = (o - hm.to(dev)) ** 2
+                    loss = loss + d.sum() / d.numel()
+                opt_torch.zero_grad()
+                loss.backward()
+                opt_torch.step()
+                last = float(loss.detach())
+            n_img += img.shape[0] * world
+            if rank == 0 and (i % opt.print_freq == 0):
+                print("epoch %d iter %d loss %.6f" % (epoch, i, last))
+        history.append(last)
+        if rank == 0:
+            print("epoch %d done: loss %.6f, %.1f images/s" % (epoch, last, n_img / (time.time() - t0)))
+    return history
+
+
+if __name__ == "__main__":
+    run(parse())

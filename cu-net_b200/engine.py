@@ -403,8 +403,11 @@ class Trainer(object):
     """
 
     def __init__(self, net, batch, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, process_group=None,
-                 world_size=1, use_graph=False):
+                 world_size=1, use_graph=False, quant=None):
+        """quant: optional BinOp / QuanOp built on ``net`` -- the step then follows the reference's quantized
+        protocol (cu-net-prev-version-bin.py:163-191): quantize -> fwd/bwd -> restore -> fix grads -> step."""
         self.net = net
+        self.quant = quant
         self.eng = net.engine(batch, device)
         self.alpha, self.eps = alpha, eps
         self.set_lr(lr)
@@ -424,9 +427,15 @@ class Trainer(object):
 
     def _fwd_bwd(self):
         e = self.eng
+        q = self.quant
+        if q is not None:
+            (q.binarization if hasattr(q, "binarization") else q.quantization)()
         e.forward(train=True)
         e.loss_and_decode(with_grad=True)
         e.backward()
+        if q is not None:
+            q.restore()
+            (q.updateBinaryGradWeight if hasattr(q, "updateBinaryGradWeight") else q.updateQuanGradWeight)()
 
     def _capture(self):
         # warm-up on a side stream (sets kernel attributes, allocates nothing afterwards), then capture
@@ -455,8 +464,8 @@ class Trainer(object):
         else:
             self._fwd_bwd()
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(e.grads, group=self.pg)       # gradients were pre-scaled by 1/world (sum == mean)
+            from .parallel import allreduce_mean
+            allreduce_mean(e.grads, self.world, self.pg)  # gradients were pre-scaled by 1/world (sum == mean)
         if self.use_graph:
             self._g_opt.replay()
         else:

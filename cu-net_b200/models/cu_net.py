@@ -111,6 +111,7 @@ class CUNetB200(nn.Module):
                 old = getattr(mod, leaf)
                 view.copy_(old.data)
                 prm = nn.Parameter(view, requires_grad=True)
+                prm.grad = eng.grads[o:o + n].view(shape)      # .grad aliases the flat gradient bucket
                 setattr(mod, leaf, prm)
             elif s.kind in ("bn_mean", "bn_var"):
                 o, n, shape = eng.b_off[s.name]
