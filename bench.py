@@ -75,31 +75,53 @@ class ClockSampler(threading.Thread):
                     samples=len(sm))
 
 
-def cpu_reference(cfg, sample_batch, iters, warmup=1):
-    """The reference's algorithm (oracle port of models/cu_net.py + cu-net.py:175-183 loss/backward/RMSprop) on
-    the host cores.  Returns (images_per_sec, cores)."""
+def _cpu_step_fn(cfg, batch):
     import torch
     from oracle import cunet_oracle, synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     state = cunet_oracle.init_state(cfg["class_num"], cfg["layer_num"], cfg["order"], seed=0)
     net = cunet_oracle.OracleCUNet(state, cfg["class_num"], cfg["layer_num"], cfg["order"], cfg["loss_num"])
-    img, hm = synthetic.make_inputs(sample_batch, cfg["class_num"], seed=0)
+    img, hm = synthetic.make_inputs(batch, cfg["class_num"], seed=0)
     params = net.parameters()
     sq = [torch.zeros_like(p) for p in params]
-    times = []
-    for it in range(warmup + iters):
-        t0 = time.perf_counter()
+
+    def step():
         net.zero_grad()
         loss = cunet_oracle.multi_loss_mse(net(img), hm)
         loss.backward()
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
         cunet_oracle.rmsprop_step(params, grads, sq, 2.5e-4)
+    return step
+
+
+def cpu_reference(cfg, sample_batch, iters, warmup=1):
+    """The reference's algorithm (oracle port of models/cu_net.py + cu-net.py:175-183 loss/backward/RMSprop) on
+    the host cores.  The thread count is the fastest of {all cores, 64, 32, 16} on a one-image CU-Net-2 probe
+    step (oneDNN/ATen oversubscribe badly on 100+ core hosts for these small convolutions).
+    Returns (images_per_sec, threads_used)."""
+    import torch
+    cores = os.cpu_count() or 1
+    probe_cfg = dict(cfg, layer_num=2, loss_num=2)
+    best, best_t = None, cores
+    for t in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+        torch.set_num_threads(t)
+        fn = _cpu_step_fn(probe_cfg, 1)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, best_t = dt, t
+    torch.set_num_threads(best_t)
+    step = _cpu_step_fn(cfg, sample_batch)
+    times = []
+    for it in range(warmup + iters):
+        t0 = time.perf_counter()
+        step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     times.sort()
-    return sample_batch / times[len(times) // 2], cores
+    return sample_batch / times[len(times) // 2], best_t
 
 
 def op_bytes(eng, op, kind):
