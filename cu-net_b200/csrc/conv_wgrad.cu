@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(WG_THREADS, StageGeom<T>::MIN_CTAS) conv_wgrad
 }  // namespace cunet
 using namespace cunet;
 
+int cunet_conv_wgrad3x3_launch(const cunet_conv_wgrad_params* p, cudaStream_t st);  // conv_wgrad3x3.cu
+
 extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) {
   if (!p) return cunet_fail("conv_wgrad: null params");
   if (p->in.nseg < 1 || p->in.nseg > CUNET_MAX_SEG) return cunet_fail("conv_wgrad: bad nseg");
@@ -232,6 +234,8 @@ extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) 
   if (p->dy.C > 128 || p->Cout > 128) return cunet_fail("conv_wgrad: Cout > 128");
   const long M = (long)p->N * p->H * p->W;
   if (M <= 0) return 0;
+  if (p->taps == 9 && cin <= 128 && p->dy.C == 32 && p->dw_cin == 0)   // the network's 3x3: all taps in one CTA
+    return cunet_conv_wgrad3x3_launch(p, reinterpret_cast<cudaStream_t>(stream));
   const int kbe = p->dtype == CUNET_BF16 ? 64 : 32;
   const int R = p->dtype == CUNET_BF16 ? 64 : 32;
   const int npad = ((p->dy.C + kbe - 1) / kbe) * kbe;  // whole MN groups of the gradient operand

@@ -271,8 +271,10 @@ class Engine(object):
             return mp
         self.mse_train, self.mse_eval = mse_params(True), mse_params(False)
 
-        # backward
-        calls = []
+        # backward: the dgrad chain is the critical path; every wgrad only feeds the optimizer, so the wgrads run
+        # on a side stream (a parallel branch of the captured graph) and fill the SMs the small low-resolution
+        # dgrads leave idle
+        calls, wcalls = [], []
         for op, flags in p.backward_schedule():
             dp = L.ConvDgradParams()
             self._concat(dp.inp, op, 1)
@@ -292,7 +294,7 @@ class Engine(object):
             self._grad_src(wp.dy, op.out, op)
             wp.N, wp.H, wp.W, wp.taps, wp.Cout = N, op.res, op.res, op.taps, op.cout
             wp.dw, wp.nsplit, wp.dtype, wp.dw_cin = self._gp(op.conv + ".weight"), 0, self.dtype, 0
-            calls.append((lib.cunet_conv_wgrad, wp))
+            wcalls.append((len(calls) - 1, lib.cunet_conv_wgrad, wp))      # may start once dgrad #k may start
             self.call_index[(op.name, "wgrad")] = wp
         # stem backward: parameter-gradient reduction, dy, conv0 wgrad
         for phase in (0, 1):
@@ -319,6 +321,9 @@ class Engine(object):
         wp.dw, wp.nsplit, wp.dtype, wp.dw_cin = self._gp("features.conv0.weight"), 0, self.dtype, 147
         calls.append((lib.cunet_conv_wgrad, wp))
         self.bwd_calls = calls
+        self.bwd_wgrad_calls = wcalls
+        self.side_stream = torch.cuda.Stream(device=self.device)
+        self._evpool = [torch.cuda.Event() for _ in range(len(wcalls) + 1)]
 
     # ------------------------------------------------------------------------------------------ execution
     def _run(self, calls):
@@ -366,7 +371,37 @@ class Engine(object):
     def backward(self):
         """dLoss/dhead must be in self.G[head] (written by loss_and_decode or by the autograd bridge)."""
         self.grads.zero_()
-        self._run(self.bwd_calls)
+        main = torch.cuda.current_stream()
+        side = self.side_stream
+        probes = getattr(self, "probes", None)
+        if probes:                      # instrumentation mode (bench probes): plain serial order
+            k = 0
+            for i, (fn, prm) in enumerate(self.bwd_calls):
+                self._run([(fn, prm)])
+                while k < len(self.bwd_wgrad_calls) and self.bwd_wgrad_calls[k][0] == i:
+                    self._run([self.bwd_wgrad_calls[k][1:]])
+                    k += 1
+            return
+        st_main = C.c_void_p(main.cuda_stream)
+        st_side = C.c_void_p(side.cuda_stream)
+        k = 0
+        for i, (fn, prm) in enumerate(self.bwd_calls):
+            # wgrad of this op needs exactly what its dgrad needs: everything launched so far on the main stream
+            if k < len(self.bwd_wgrad_calls) and self.bwd_wgrad_calls[k][0] == i:
+                ev = self._evpool[k]
+                ev.record(main)
+                side.wait_event(ev)
+                _, wfn, wprm = self.bwd_wgrad_calls[k]
+                rc = wfn(C.byref(wprm), st_side)
+                if rc != 0:
+                    L.check(rc, wfn.__name__)
+                k += 1
+            rc = fn(C.byref(prm), st_main)
+            if rc != 0:
+                L.check(rc, fn.__name__)
+        ev = self._evpool[-1]
+        ev.record(side)
+        main.wait_event(ev)
 
     def optimizer_step(self, alpha=0.99, eps=1e-8):
         lib = L.load()
@@ -389,7 +424,7 @@ class Engine(object):
 
     # kernels launched per call, for bench.py's gpu_launches
     def launches_per_train_step(self):
-        return 2 + len(self.fwd_train) + 1 + 2 + len(self.bwd_calls) + 1
+        return 2 + len(self.fwd_train) + 1 + 2 + len(self.bwd_calls) + len(self.bwd_wgrad_calls) + 1
 
 
 class Trainer(object):
@@ -409,6 +444,7 @@ class Trainer(object):
         self.net = net
         self.quant = quant
         self.eng = net.engine(batch, device)
+        net.bind_grads()
         self.alpha, self.eps = alpha, eps
         self.set_lr(lr)
         self.pg, self.world = process_group, world_size

@@ -48,8 +48,11 @@ class _HeadsFn(torch.autograd.Function):
                 buf[..., :p.class_num].copy_(g.permute(0, 2, 3, 1))
         eng.backward()
         grads = []
+        base = eng.grads.data_ptr()
         for name, prm in net._param_items:
             o, n, shape = eng.p_off[name]
+            if prm.grad is not None and prm.grad.data_ptr() == base + 4 * o:
+                prm.grad = None      # .grad was aliased to the flat bucket by bind_grads(): hand autograd a fresh tensor
             grads.append(eng.grads[o:o + n].view(shape).clone())
         return (None, None) + tuple(grads)
 
@@ -111,7 +114,6 @@ class CUNetB200(nn.Module):
                 old = getattr(mod, leaf)
                 view.copy_(old.data)
                 prm = nn.Parameter(view, requires_grad=True)
-                prm.grad = eng.grads[o:o + n].view(shape)      # .grad aliases the flat gradient bucket
                 setattr(mod, leaf, prm)
             elif s.kind in ("bn_mean", "bn_var"):
                 o, n, shape = eng.b_off[s.name]
@@ -137,6 +139,14 @@ class CUNetB200(nn.Module):
                 self._store = eng
             self._engines[key] = eng
         return eng
+
+    def bind_grads(self):
+        """Alias every parameter's ``.grad`` to its slice of the engine's flat gradient bucket (the fused Trainer
+        path: BinOp / QuanOp and torch optimizers then see the gradients the backward kernels wrote)."""
+        eng = self._store
+        for name, prm in self._param_items:
+            o, n, shape = eng.p_off[name]
+            prm.grad = eng.grads[o:o + n].view(shape)
 
     def cuda(self, device=None):
         # parameters live in the engine's device buffers once the first engine exists
