@@ -219,13 +219,36 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
     }
     // one row (or one 2x2 window of an upsampled source) per iteration; kept deliberately light on registers:
     // at 2 CTAs / SM a deeper register prefetch spills and measured slower ("dgrad epilogue")
-    for (int j = 0; j < nrow_it; ++j) {
-      const int r = sg.up ? 4 * (rg + 8 * j) : rg + 8 * j;
+    // software pipeline of depth 1: the global loads of row j+1 are issued before row j is processed
+    auto row_of = [&](int j, long& row, int& r) -> bool {
+      r = sg.up ? 4 * (rg + 8 * j) : rg + 8 * j;
       const int rd = tail->rows.rd[r];
-      if (rd < 0) continue;
-      const long row = sg.up ? tail->rows.ru[r] : rd;
+      row = sg.up ? tail->rows.ru[r] : rd;
+      return rd >= 0;
+    };
+    Raw4<T> xn, on;
+    long row_n = 0;
+    int r_n = 0;
+    bool ok_n = row_of(0, row_n, r_n);
+    if (ok_n) {
+      xn.load(src + row_n * sg.ld + cl);
+      if (ga.accumulate) on.load(G + row_n * ga.ld + cl);
+    }
+    for (int j = 0; j < nrow_it; ++j) {
+      const Raw4<T> xc = xn, oc = on;
+      const long row = row_n;
+      const int r = r_n;
+      const bool ok = ok_n;
+      if (j + 1 < nrow_it) {
+        ok_n = row_of(j + 1, row_n, r_n);
+        if (ok_n) {
+          xn.load(src + row_n * sg.ld + cl);
+          if (ga.accumulate) on.load(G + row_n * ga.ld + cl);
+        }
+      }
+      if (!ok) continue;
       float gv[4] = {0, 0, 0, 0}, xv[4];
-      load4<T>(src + row * sg.ld + cl, xv);
+      xc.get(xv);
       if (!sg.up) {
         const float4 a = *reinterpret_cast<const float4*>(ep + r * LD_EP + quad * 4);
         const float av[4] = {a.x, a.y, a.z, a.w};
@@ -253,14 +276,13 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
           }
         }
       }
-      T* gp = G + row * ga.ld + cl;
       if (ga.accumulate) {
         float ov[4];
-        load4<T>(gp, ov);
+        oc.get(ov);
 #pragma unroll
         for (int e = 0; e < 4; ++e) gv[e] += ov[e];
       }
-      store4<T>(gp, gv);  // gv <- values as stored
+      store4<T>(G + row * ga.ld + cl, gv);  // gv <- values as stored
       if (ga.gstats) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
