@@ -15,6 +15,7 @@
 //   source the per-channel (sum G, sum G*xhat) that the producer's backward needs.
 #include "loaders.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace cunet {
 
@@ -332,6 +333,8 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
 }  // namespace cunet
 using namespace cunet;
 
+int cunet_conv_dgrad_v2_try(const cunet_conv_dgrad_params* p, cudaStream_t st);  // conv_dgrad_v2.cu
+
 extern "C" int cunet_conv_dgrad(const cunet_conv_dgrad_params* p, void* stream) {
   if (!p) return cunet_fail("conv_dgrad: null params");
   if (p->in.nseg < 1 || p->in.nseg > CUNET_MAX_SEG) return cunet_fail("conv_dgrad: bad nseg");
@@ -348,6 +351,14 @@ extern "C" int cunet_conv_dgrad(const cunet_conv_dgrad_params* p, void* stream) 
   if (up && ((p->H | p->W) & 1)) return cunet_fail("conv_dgrad: upsampled source needs even H, W");
   const long M = (long)p->N * p->H * p->W;
   if (M <= 0) return 0;
+  {
+    // bf16 1x1: persistent bulk-copy kernel; everything else (fp32 split mode, 3x3, unusual layouts): this file
+    static const bool v1_only = getenv("CUNET_DGRAD_V1") != nullptr;
+    if (!v1_only) {
+      const int r = cunet_conv_dgrad_v2_try(p, reinterpret_cast<cudaStream_t>(stream));
+      if (r != 0) return r < 0 ? r : 0;
+    }
+  }
   const long tiles = up ? (M / 4 + 31) / 32 : (M + 127) / 128;
   dim3 grid((unsigned)tiles, (unsigned)((cin + 127) / 128));
   const size_t smem = DG_STAGES * (p->dtype == CUNET_BF16 ? StageGeom<bf16>::BYTES : StageGeom<float>::BYTES) +

@@ -1,0 +1,483 @@
+// Backward-data of the fused 1x1 conv, second generation (bf16): persistent, warp-specialised, every global
+// access a 1-D TMA bulk copy.  Same contract as conv_dgrad.cu (cunet_conv_dgrad_params); see that file for the math.
+//
+// Why: the round-1 kernel spent its time in serial global-load chains (loader phase, then 16 dependent
+// load -> compute -> read-modify-write round trips per epilogue thread) with only 2 CTAs per SM to overlap them
+// (ncu: 50 % long-scoreboard stalls, 8 % DRAM).  Here no thread ever waits on a global load:
+//   * every operand tile of this kernel is a CONTIGUOUS block of an NHWC tensor (a 128-pixel tile of a tensor is
+//     128 consecutive rows), so the landing producer moves it with cp.async.bulk into a 4-slot shared-memory ring,
+//     running up to four jobs ahead of its consumers; results leave the same way (bulk store from the slot);
+//   * transposed GEMM: D[128 channels][128 pixels] = Wt[128 ch][Kg] * dT[128 px][Kg]^T, so an epilogue thread owns
+//     ONE input channel (its TMEM lane) and walks the pixels: the per-channel sums (dbeta, dgamma, sum G,
+//     sum G*xhat) are plain register accumulators and the 2x2 sum of an upsampled source is four consecutive
+//     columns -- no cross-lane reductions, no fp32 staging tile;
+//   * one persistent CTA per SM; roles: landing producer | weight producer | MMA issuer | 4 dT-transform warps
+//     | 8 epilogue warps; TMEM accumulator double-buffered so the MMAs of item i+1 overlap the epilogue of item i.
+#include "loaders.cuh"
+#include "host_util.h"
+
+namespace cunet {
+
+// optional in-kernel timeline (tools/trace_dgrad.py): CTA 0 records clock64() at role milestones
+__device__ long long* g_d2_trace = nullptr;
+#define D2_TRACE(slot_expr)                                                   \
+  do {                                                                        \
+    if (trace != nullptr && blockIdx.x == 0) trace[(slot_expr)] = clock64(); \
+  } while (0)
+
+constexpr int D2_THREADS = 480;  // 15 warps
+constexpr int D2_NSLOT = 4;
+constexpr int D2_SLOT = 32768;
+constexpr int D2_A_OFF = D2_NSLOT * D2_SLOT;  // dT operand: 2 K blocks x 16 KB
+constexpr int D2_W_OFF = D2_A_OFF + 32768;    // weight chunk: 2 K blocks x 16 KB
+constexpr int D2_TAIL_OFF = D2_W_OFF + 32768;
+
+struct D2Tail {
+  // full barriers are per consumer party (A = dT transformers, B = epilogue): a party only ever sees the phases of
+  // its own jobs, so a 1-bit parity wait can never alias a phase completed for the other party
+  uint64_t slot_fullA[D2_NSLOT], slot_fullB[D2_NSLOT], slot_empty[D2_NSLOT];
+  uint64_t dt_ready, dt_free, w_full, w_free;
+  uint64_t acc_full[2], acc_free[2];
+  uint32_t tmem_base;
+  int rows_rd[4][128];
+  int rows_ru[4][128];
+  int rows_pos[4][128];  // position inside the 2x2 window: (h & 1) * 2 + (w & 1)
+  BnSmem bn;
+  GradSmem gc;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// geometry of one tile: first row / row count of its full-resolution block and of its half-resolution block
+struct TileSpan {
+  int full0, nfull, low0, nlow;
+};
+__device__ __forceinline__ TileSpan tile_span(const PixGeom& g, int tile, int grouped) {
+  TileSpan s;
+  if (!grouped) {
+    // raster tile; for power-of-two W <= 64 its 2x2 windows are the 32 consecutive half-resolution rows 32*tile..
+    s.full0 = tile * 128;
+    s.nfull = min(128, g.M - s.full0);
+    s.low0 = tile * 32;
+    s.nlow = s.nfull >> 2;
+  } else {
+    const int nwin = g.M >> 2;
+    s.low0 = tile * 32;
+    s.nlow = min(32, nwin - s.low0);
+    int n, hh, ww;
+    pix_split(s.low0, g.H >> 1, g.W >> 1, n, hh, ww);
+    s.full0 = (n * g.H + 2 * hh) * g.W + 2 * ww;  // ww == 0 for W <= 64 (whole window rows per tile)
+    s.nfull = 4 * s.nlow;
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __grid_constant__ cunet_conv_dgrad_params p,
+                                                                       int ntiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  D2Tail* tail = reinterpret_cast<D2Tail*>(smem + D2_TAIL_OFF);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Cin = concat_cin(p.in);
+  const int nchunk = (Cin + 127) >> 7;
+  int grouped = 0;
+  for (int s = 0; s < p.in.nseg; ++s) grouped |= p.in.seg[s].up;
+  const int nkb = (p.CoutPad + 63) >> 6;  // K blocks of the Cout contraction (1 or 2)
+  PixGeom geom;
+  geom.N = p.N; geom.H = p.H; geom.W = p.W; geom.M = p.N * p.H * p.W;
+  const int ldo = p.dy.ld * 2;  // bytes per row of G_out / T_out
+  long long* trace = g_d2_trace;
+
+  if (tid == 0) {
+    for (int s = 0; s < D2_NSLOT; ++s) {
+      mbar_init(&tail->slot_fullA[s], 1);
+      mbar_init(&tail->slot_fullB[s], 1);
+      mbar_init(&tail->slot_empty[s], 1);
+    }
+    mbar_init(&tail->dt_ready, 4);
+    mbar_init(&tail->dt_free, 1);
+    mbar_init(&tail->w_full, 1);
+    mbar_init(&tail->w_free, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->acc_full[b], 1);
+      mbar_init(&tail->acc_free[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tail->tmem_base, 256);
+  compute_bn_coefs(p.in, &tail->bn, nchunk * 128, tid, D2_THREADS);
+  compute_grad_coefs(p.dy, &tail->gc, tid, D2_THREADS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  // ---- job enumeration shared by all roles (per tile): G_out, [T_out], [idx], then per chunk and per segment
+  //      piece of the chunk: x, G_src.  Job j lives in slot j % 4.
+  auto seg_chunk = [&](int s) { return tail->bn.seg_start[s] >> 7; };
+
+  if (warp == 0) {
+    // ============================================================== landing producer
+    if (lane == 0) {
+      uint32_t jn = 0;
+      auto land = [&](const void* src, uint32_t bytes, bool party_b) {
+        const int slot = jn & 3;
+        uint64_t* full = party_b ? &tail->slot_fullB[slot] : &tail->slot_fullA[slot];
+        mbar_wait(&tail->slot_empty[slot], ((jn >> 2) & 1) ^ 1);
+        if (bytes) {
+          mbar_arrive_expect_tx(full, bytes);
+          bulk_g2s(smem + slot * D2_SLOT, src, bytes, full);
+        } else {
+          mbar_arrive(full);
+        }
+        ++jn;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileSpan sp = tile_span(geom, tile, grouped);
+        const int r0 = p.dy.pooled ? sp.low0 : sp.full0, nr = p.dy.pooled ? sp.nlow : sp.nfull;
+        land(reinterpret_cast<const char*>(p.dy.g) + (long)r0 * ldo, (uint32_t)(nr * ldo), false);
+        if (p.dy.mode == 1) land(reinterpret_cast<const char*>(p.dy.t) + (long)r0 * ldo, (uint32_t)(nr * ldo), false);
+        if (p.dy.pooled) land(p.dy.pool_idx + (long)r0 * p.dy.C, (uint32_t)(nr * p.dy.C), false);
+        for (int c = 0; c < nchunk; ++c) {
+          for (int s = 0; s < p.in.nseg; ++s) {
+            if (seg_chunk(s) != c) continue;
+            const cunet_seg& sg = p.in.seg[s];
+            const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
+            const uint32_t bytes = (uint32_t)(nx * sg.C * 2);
+            land(reinterpret_cast<const char*>(sg.ptr) + (long)x0 * sg.C * 2, p.gacc[s].G ? bytes : 0u, true);
+            land(reinterpret_cast<const char*>(p.gacc[s].G) + (long)x0 * sg.C * 2,
+                 (p.gacc[s].G && p.gacc[s].accumulate) ? bytes : 0u, true);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================== weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t wbytes = (uint32_t)nkb * 16384u;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunk; ++c, ++it) {
+          mbar_wait(&tail->w_free, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&tail->w_full, wbytes);
+          bulk_g2s(smem + D2_W_OFF, reinterpret_cast<const char*>(p.wpack_dgrad) + (size_t)c * wbytes, wbytes,
+                   &tail->w_full);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(Elem<bf16>::FMT, 128, 128, 0, 0);
+      const uint32_t a_w = smem_u32(smem + D2_W_OFF), b_dt = smem_u32(smem + D2_A_OFF);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        mbar_wait(&tail->dt_ready, tl & 1);
+        for (int c = 0; c < nchunk; ++c, ++it) {
+          const uint32_t buf = it & 1;
+          if (it < 24) D2_TRACE(256 + it * 4 + 0);
+          mbar_wait(&tail->acc_free[buf], ((it >> 1) & 1) ^ 1);
+          if (it < 24) D2_TRACE(256 + it * 4 + 1);
+          mbar_wait(&tail->w_full, it & 1);
+          tc_fence_after();
+          if (it < 24) D2_TRACE(256 + it * 4 + 2);
+          for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma<bf16>(tmem + buf * 128, make_sdesc(a_w + kb * 16384 + kk * 32, 16, 1024),
+                         make_sdesc(b_dt + kb * 16384 + kk * 32, 16, 1024), idesc, (uint32_t)((kb | kk) != 0));
+          }
+          tc_commit(&tail->w_free);
+          tc_commit(&tail->acc_full[buf]);
+        }
+        tc_commit(&tail->dt_free);
+      }
+    }
+  } else if (warp < 7) {
+    // ============================================================== dT transformers (warps 3-6, 128 threads)
+    const int t = tid - 96;
+    const int cc = t & 15, rbase = t >> 4;  // 16 chunk columns x 8 rows per pass
+    GradCoef<bf16> cf;
+    cf.load(&tail->gc, (cc * 8) & 127);
+    const bool col_ok = cc * 8 < p.dy.C;
+    uint32_t jn = 0, tl = 0;
+    uint32_t useA = 0;  // bit s: parity of the number of party-A jobs seen so far on slot s
+    auto next_a = [&](int& slot, uint32_t& ph) {
+      slot = jn & 3;
+      ph = (useA >> slot) & 1;
+      useA ^= 1u << slot;
+      ++jn;
+    };
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      // row table of this tile (thread t <-> tile row t)
+      {
+        int n = 0, h = 0, w = 0;
+        const bool valid = tile_row_pixel(geom, tile, t, grouped, n, h, w);
+        tail->rows_rd[tl & 3][t] = valid ? (n * geom.H + h) * geom.W + w : -1;
+        tail->rows_ru[tl & 3][t] = valid ? (n * (geom.H >> 1) + (h >> 1)) * (geom.W >> 1) + (w >> 1) : 0;
+        tail->rows_pos[tl & 3][t] = ((h & 1) << 1) | (w & 1);
+      }
+      int sg_slot, st_slot = 0, si_slot = 0;
+      uint32_t sg_ph, st_ph = 0, si_ph = 0;
+      next_a(sg_slot, sg_ph);
+      if (p.dy.mode == 1) next_a(st_slot, st_ph);
+      if (p.dy.pooled) next_a(si_slot, si_ph);
+      for (int c = 0; c < nchunk; ++c)
+        for (int s = 0; s < p.in.nseg; ++s)
+          if (seg_chunk(s) == c) jn += 2;
+      if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 0);
+      mbar_wait(&tail->slot_fullA[sg_slot], sg_ph);
+      if (p.dy.mode == 1) mbar_wait(&tail->slot_fullA[st_slot], st_ph);
+      if (p.dy.pooled) mbar_wait(&tail->slot_fullA[si_slot], si_ph);
+      if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 1);
+      mbar_wait(&tail->dt_free, (tl & 1) ^ 1);  // MMAs of the previous tile no longer read the operand buffer
+      if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 2);
+      named_bar_sync(1, 128);                   // row table complete
+      const uint8_t* rg = smem + sg_slot * D2_SLOT;
+      const uint8_t* rt = smem + st_slot * D2_SLOT;
+      const uint8_t* ri = smem + si_slot * D2_SLOT;
+      const int* rd = tail->rows_rd[tl & 3];
+      const int* ru = tail->rows_ru[tl & 3];
+      const int* rpos = tail->rows_pos[tl & 3];
+      const int rd0 = rd[0], ru0 = ru[0];
+      const uint32_t abase = smem_u32(smem + D2_A_OFF);
+      if (cc < nkb * 8) {
+#pragma unroll 4
+        for (int ps = 0; ps < 16; ++ps) {
+          const int r = rbase + 8 * ps;
+          uint4 o = make_uint4(0, 0, 0, 0), lo;
+          const int rdr = rd[r];
+          if (col_ok && rdr >= 0) {
+            GradRaw<bf16> raw;
+            const int loc = p.dy.pooled ? (ru[r] - ru0) : (rdr - rd0);
+            raw.g = *reinterpret_cast<const uint4*>(rg + loc * ldo + cc * 16);
+            if (p.dy.mode == 1) raw.t = *reinterpret_cast<const uint4*>(rt + loc * ldo + cc * 16);
+            if (p.dy.pooled) {
+              const uint2 iv = *reinterpret_cast<const uint2*>(ri + loc * p.dy.C + cc * 8);
+              raw.idx[0] = iv.x;
+              raw.idx[1] = iv.y;
+              raw.pos = (uint32_t)rpos[r];
+            }
+            o = cf.apply(p.dy, raw, lo);
+          }
+          sts128(abase + (cc >> 3) * 16384 + tile_off(r, cc & 7), o);
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (t == 0) {  // landing slots of G_out / T_out / idx are free again
+        mbar_arrive(&tail->slot_empty[sg_slot]);
+        if (p.dy.mode == 1) mbar_arrive(&tail->slot_empty[st_slot]);
+        if (p.dy.pooled) mbar_arrive(&tail->slot_empty[si_slot]);
+      }
+      if (lane == 0) mbar_arrive(&tail->dt_ready);
+      if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 3);
+    }
+  } else {
+    // ============================================================== epilogue (warps 7-14, 256 threads)
+    const int e = warp - 7;
+    const int qd = warp & 3, hf = e >> 2;  // TMEM lane quarter (hardware: warp % 4), pixel-column half
+    const int k = qd * 32 + lane;          // channel within the chunk
+    const int et = tid - 224;              // 0..255
+    uint32_t jn = 0, it = 0, tl = 0;
+    uint32_t useB = 0;  // bit s: parity of the number of party-B jobs seen so far on slot s (every warp counts every job)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      ++jn;
+      if (p.dy.mode == 1) ++jn;
+      if (p.dy.pooled) ++jn;
+      const TileSpan sp = tile_span(geom, tile, grouped);
+      for (int c = 0; c < nchunk; ++c, ++it) {
+        const uint32_t buf = it & 1;
+        const int kg = c * 128 + k;
+        // this thread's piece (warp-uniform): the segment that contains concat channel kg
+        int ps = -1, pj = 0;
+        {
+          int j = 0;
+          for (int s = 0; s < p.in.nseg; ++s) {
+            if (seg_chunk(s) != c) continue;
+            if (kg >= tail->bn.seg_start[s] && kg < tail->bn.seg_start[s + 1]) { ps = s; pj = j; }
+            ++j;
+          }
+        }
+        const uint32_t jx = jn + 2 * pj, jg = jx + 1;
+        float a_db = 0.f, a_dg = 0.f, a_g = 0.f, a_gt = 0.f;
+        if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 0);
+        mbar_wait(&tail->acc_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+        if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 1);
+        if (ps >= 0 && p.gacc[ps].G != nullptr) {
+          const cunet_seg& sg = p.in.seg[ps];
+          const cunet_gacc& ga = p.gacc[ps];
+          // parity = number of party-B jobs that used the slot before this one (pieces before pj in this chunk
+          // occupy other slots: a chunk has at most two pieces = four distinct slots)
+          mbar_wait(&tail->slot_fullB[jx & 3], (useB >> (jx & 3)) & 1);
+          mbar_wait(&tail->slot_fullB[jg & 3], (useB >> (jg & 3)) & 1);
+          if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 2);
+          const bf16* X = reinterpret_cast<const bf16*>(smem + (jx & 3) * D2_SLOT);
+          bf16* Gs = reinterpret_cast<bf16*>(smem + (jg & 3) * D2_SLOT);
+          const int kl = kg - tail->bn.seg_start[ps];
+          const int Cp = sg.C;
+          const float sc = tail->bn.scale[kg], sh = tail->bn.shift[kg], mu = tail->bn.mean[kg], is = tail->bn.istd[kg];
+          const float gm = p.in.gamma[kg];
+          const int* rd = tail->rows_rd[tl & 3];
+          const int* ru = tail->rows_ru[tl & 3];
+          const int rd0 = rd[0], ru0 = ru[0];
+          for (int g8 = 0; g8 < 8; ++g8) {
+            const int col0 = hf * 64 + g8 * 8;
+            float v[8];
+            tmem_ld8(tmem + buf * 128 + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
+            if (!sg.up) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int rdr = rd[col0 + q];
+                if (rdr < 0) continue;
+                const int off = (rdr - rd0) * Cp + kl;
+                const float x = __bfloat162float(X[off]);
+                const float dz = fmaf(x, sc, sh) > 0.f ? v[q] : 0.f;
+                const float xh = (x - mu) * is;
+                a_db += dz;
+                a_dg += dz * xh;
+                float gv = gm * dz;
+                if (ga.accumulate) gv += __bfloat162float(Gs[off]);
+                const bf16 gb = __float2bfloat16_rn(gv);
+                Gs[off] = gb;
+                if (ga.gstats) {
+                  const float gf = __bfloat162float(gb);
+                  a_g += gf;
+                  a_gt += gf * xh;
+                }
+              }
+            } else {
+              // upsampled source: columns 4w..4w+3 are the four children of low-resolution pixel w
+#pragma unroll
+              for (int wq = 0; wq < 2; ++wq) {
+                if (rd[col0 + 4 * wq] < 0) continue;
+                const int off = (ru[col0 + 4 * wq] - ru0) * Cp + kl;
+                const float x = __bfloat162float(X[off]);
+                const float xh = (x - mu) * is;
+                const bool on = fmaf(x, sc, sh) > 0.f;
+                float dzs = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) dzs += on ? v[4 * wq + ch] : 0.f;
+                a_db += dzs;
+                a_dg += dzs * xh;
+                float gv = gm * dzs;
+                if (ga.accumulate) gv += __bfloat162float(Gs[off]);
+                const bf16 gb = __float2bfloat16_rn(gv);
+                Gs[off] = gb;
+                if (ga.gstats) {
+                  const float gf = __bfloat162float(gb);
+                  a_g += gf;
+                  a_gt += gf * xh;
+                }
+              }
+            }
+          }
+          atomicAdd(p.dbeta + kg, a_db);
+          atomicAdd(p.dgamma + kg, a_dg);
+          if (ga.gstats) {
+            atomicAdd(ga.gstats + kl, (double)a_g);
+            atomicAdd(ga.gstats + Cp + kl, (double)a_gt);
+          }
+        }
+        if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 3);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->acc_free[buf]);  // TMEM buffer drained by this warp
+        fence_proxy_async();
+        named_bar_sync(2, 256);  // every G slot of this chunk is final
+        if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 4);
+        if (et == 0) {
+          int j = 0;
+          for (int s = 0; s < p.in.nseg; ++s) {
+            if (seg_chunk(s) != c) continue;
+            const cunet_seg& sg = p.in.seg[s];
+            const uint32_t jgs = jn + 2 * j + 1;
+            if (p.gacc[s].G != nullptr) {
+              const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
+              bulk_s2g(reinterpret_cast<char*>(p.gacc[s].G) + (long)x0 * sg.C * 2, smem + (jgs & 3) * D2_SLOT,
+                       (uint32_t)(nx * sg.C * 2));
+            }
+            ++j;
+          }
+          bulk_commit();
+          bulk_wait_read0();  // the slots may be overwritten once the stores have read them
+          if (it < 24) D2_TRACE(64 + it * 8 + 5);
+          for (int q = 0; q < 2 * j; ++q) mbar_arrive(&tail->slot_empty[(jn + q) & 3]);
+        }
+        int npc = 0;
+        for (int s = 0; s < p.in.nseg; ++s) npc += (seg_chunk(s) == c);
+        for (int q = 0; q < 2 * npc; ++q) useB ^= 1u << ((jn + q) & 3);
+        jn += 2 * npc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace cunet
+using namespace cunet;
+
+// debug: device buffer of >= 512 long longs receiving CTA 0's timeline (NULL disables)
+extern "C" int cunet_debug_dgrad_trace(void* buf) {
+  long long* b = reinterpret_cast<long long*>(buf);
+  cudaError_t e = cudaMemcpyToSymbol(g_d2_trace, &b, sizeof(b));
+  if (e != cudaSuccess) return cunet_fail_cuda("dgrad_trace", e);
+  return 0;
+}
+
+// Returns 1 when the v2 kernel handled the call, 0 when the caller must use the generic kernel, <0 on error.
+int cunet_conv_dgrad_v2_try(const cunet_conv_dgrad_params* p, cudaStream_t st) {
+  if (p->dtype != CUNET_BF16 || p->taps != 1) return 0;
+  if (p->dy.ld != p->dy.C || p->dy.C > 128 || (p->dy.C & 7)) return 0;
+  if (p->CoutPad > 128) return 0;
+  int cin = 0, up = 0, pieces_max = 0;
+  int per_chunk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < p->in.nseg; ++s) {
+    const cunet_seg& sg = p->in.seg[s];
+    if (sg.ld != sg.C || (sg.C != 32 && sg.C != 64 && sg.C != 128)) return 0;
+    if ((cin >> 7) != ((cin + sg.C - 1) >> 7)) return 0;  // a segment must not straddle a 128-channel chunk
+    if (p->gacc[s].G && p->gacc[s].ld != sg.C) return 0;
+    if ((cin >> 7) >= 8) return 0;
+    per_chunk[cin >> 7]++;
+    cin += sg.C;
+    up |= sg.up;
+  }
+  for (int c = 0; c < 8; ++c) pieces_max = per_chunk[c] > pieces_max ? per_chunk[c] : pieces_max;
+  if (pieces_max > 2) return 0;  // 4 landing slots: x and G of at most two pieces per chunk are resident together
+  if (cin > MAX_CIN) return 0;
+  if (up || p->dy.pooled) {
+    const int W = p->W, H = p->H;
+    if ((W & (W - 1)) || (H & (H - 1)) || W > 64 || W < 2 || H < 2) return 0;
+  }
+  const long M = (long)p->N * p->H * p->W;
+  if (M <= 0) return 1;
+  const int ntiles = (int)(up ? (M / 4 + 31) / 32 : (M + 127) / 128);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int grid = ntiles < sms ? ntiles : sms;
+  const size_t smem = D2_TAIL_OFF + sizeof(D2Tail) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv_dgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_dgrad_v2 attr", e);
+  conv_dgrad_v2_kernel<<<grid, D2_THREADS, smem, st>>>(*p, ntiles);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_dgrad_v2 launch", e);
+  return 1;
+}

@@ -122,6 +122,9 @@ typedef struct {
 } cunet_conv_dgrad_params;
 
 int cunet_conv_dgrad(const cunet_conv_dgrad_params* p, void* stream);
+/* debug aid: device buffer (>= 512 int64) that receives CTA 0's clock64() timeline of the persistent bf16 dgrad
+ * kernel (tools/trace_dgrad.py); NULL disables. */
+int cunet_debug_dgrad_trace(void* buf);
 
 /* Backward-filter of the fused conv: dW[co][k][tap] += sum_px dY[px][co] * relu(bn(x))[px+tap][k]
  * (autograd of nn.Conv2d w.r.t. weight), accumulated into the reference-layout fp32 gradient. */

@@ -5,7 +5,10 @@ from tests.test_gpu_conv_bwd import make_case, fill_grad_src
 from tests.test_gpu_conv_fwd import fill_concat
 lib.load()
 dtype = lib.BF16
-n,h,w,seg_c,ups,cout,taps,mode = 24,64,64,[128,128,32,32],[1,0,0,0],128,1,"bn"
+import os
+n = int(os.environ.get("NB","24")); segsel = os.environ.get("SEGS","up")
+h,w,cout,taps,mode = 64,64,128,1,"bn"
+seg_c,ups = {"up":([128,128,32,32],[1,0,0,0]), "one":([128],[0]), "two":([128,32,32],[0,0,0]), "big2":([128,128],[0,0])}[segsel]
 cs = make_case(lib, dtype, n,h,w,seg_c,ups,cout,taps,mode,None)
 dev=cs["dev"]; cin=cs["cin"]
 nbytes = lib.pack_dgrad_bytes(cin, taps, cs["cout_pad"], dtype)
@@ -24,6 +27,7 @@ dg=torch.zeros(cin,device=dev); db=torch.zeros(cin,device=dev)
 p.N,p.H,p.W,p.taps=n,h,w,taps
 p.wpack_dgrad,p.Cout,p.CoutPad=wpack.data_ptr(),cout,cs["cout_pad"]
 p.dgamma,p.dbeta,p.dtype=dg.data_ptr(),db.data_ptr(),dtype
+import time; t0=time.time(); lib.conv_dgrad(p); torch.cuda.synchronize(); print("first call ok %.2fs"%(time.time()-t0))
 for _ in range(3): lib.conv_dgrad(p)
 e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); e0.record()
