@@ -124,6 +124,23 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
   // ---- job enumeration shared by all roles (per tile): G_out, [T_out], [idx], then per chunk and per segment
   //      piece of the chunk: x, G_src.  Job j lives in slot j % 4.
   auto seg_chunk = [&](int s) { return tail->bn.seg_start[s] >> 7; };
+  // Job order (identical in every role).  The dT jobs (G_out, T_out, idx) of the NEXT tile are issued before the
+  // last chunk of the current tile when there are >= 2 chunks: the last chunk of this network's concats is the
+  // one with two pieces (four slots), and landing / transforming the next tile's dT behind it left a ~4 us
+  // bubble per tile in the in-kernel timeline (tools/trace_dgrad.py).
+  int njc[4] = {0, 0, 0, 0}, prefix[4] = {0, 0, 0, 0};
+  for (int s = 0; s < p.in.nseg; ++s) njc[seg_chunk(s) & 3] += 2;
+  for (int c = 1; c < 4; ++c) prefix[c] = prefix[c - 1] + njc[c - 1];
+  const int NJ = prefix[nchunk - 1] + njc[nchunk - 1];
+  const int dTn = 1 + (p.dy.mode == 1 ? 1 : 0) + (p.dy.pooled ? 1 : 0);
+  const int ntile_cta = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int early = nchunk >= 2 ? 1 : 0;  // next tile's dT jobs go before the last chunk
+  // job index of the dT jobs of the CTA's tile #i+1, given base(i); and base(i+1)
+  auto pos_next_dt = [&](int base_i) { return base_i + (early ? NJ - njc[nchunk - 1] : NJ); };
+  auto next_base = [&](int base_i, int i) { return base_i + NJ + ((i + 1 < ntile_cta) ? dTn : 0); };
+  auto chunk_pos = [&](int base_i, int i, int c) {
+    return base_i + prefix[c] + ((early && c == nchunk - 1 && i + 1 < ntile_cta) ? dTn : 0);
+  };
 
   if (warp == 0) {
     // ============================================================== landing producer
@@ -141,13 +158,19 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
         }
         ++jn;
       };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      auto land_dt = [&](int tile) {
         const TileSpan sp = tile_span(geom, tile, grouped);
         const int r0 = p.dy.pooled ? sp.low0 : sp.full0, nr = p.dy.pooled ? sp.nlow : sp.nfull;
         land(reinterpret_cast<const char*>(p.dy.g) + (long)r0 * ldo, (uint32_t)(nr * ldo), false);
         if (p.dy.mode == 1) land(reinterpret_cast<const char*>(p.dy.t) + (long)r0 * ldo, (uint32_t)(nr * ldo), false);
         if (p.dy.pooled) land(p.dy.pool_idx + (long)r0 * p.dy.C, (uint32_t)(nr * p.dy.C), false);
+      };
+      if (ntile_cta > 0) land_dt(blockIdx.x);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const TileSpan sp = tile_span(geom, tile, grouped);
         for (int c = 0; c < nchunk; ++c) {
+          if (early && c == nchunk - 1 && i + 1 < ntile_cta) land_dt(tile + gridDim.x);
           for (int s = 0; s < p.in.nseg; ++s) {
             if (seg_chunk(s) != c) continue;
             const cunet_seg& sg = p.in.seg[s];
@@ -158,6 +181,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
                  (p.gacc[s].G && p.gacc[s].accumulate) ? bytes : 0u, true);
           }
         }
+        if (!early && i + 1 < ntile_cta) land_dt(tile + gridDim.x);
       }
     }
   } else if (warp == 1) {
@@ -210,6 +234,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     cf.load(&tail->gc, (cc * 8) & 127);
     const bool col_ok = cc * 8 < p.dy.C;
     uint32_t jn = 0, tl = 0;
+    int base_i = dTn;   // base(0)
     uint32_t useA = 0;  // bit s: parity of the number of party-A jobs seen so far on slot s
     auto next_a = [&](int& slot, uint32_t& ph) {
       slot = jn & 3;
@@ -228,12 +253,11 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
       }
       int sg_slot, st_slot = 0, si_slot = 0;
       uint32_t sg_ph, st_ph = 0, si_ph = 0;
-      next_a(sg_slot, sg_ph);
+      next_a(sg_slot, sg_ph);     // jn points at this tile's dT jobs
       if (p.dy.mode == 1) next_a(st_slot, st_ph);
       if (p.dy.pooled) next_a(si_slot, si_ph);
-      for (int c = 0; c < nchunk; ++c)
-        for (int s = 0; s < p.in.nseg; ++s)
-          if (seg_chunk(s) == c) jn += 2;
+      jn = (uint32_t)pos_next_dt(base_i);          // where the next tile's dT jobs will be
+      base_i = next_base(base_i, (int)tl);
       if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 0);
       mbar_wait(&tail->slot_fullA[sg_slot], sg_ph);
       if (p.dy.mode == 1) mbar_wait(&tail->slot_fullA[st_slot], st_ph);
@@ -289,14 +313,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     const int k = qd * 32 + lane;          // channel within the chunk
     const int et = tid - 224;              // 0..255
     uint32_t jn = 0, it = 0, tl = 0;
+    int base_i = dTn;   // base(0)
     uint32_t useB = 0;  // bit s: parity of the number of party-B jobs seen so far on slot s (every warp counts every job)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
-      ++jn;
-      if (p.dy.mode == 1) ++jn;
-      if (p.dy.pooled) ++jn;
       const TileSpan sp = tile_span(geom, tile, grouped);
       for (int c = 0; c < nchunk; ++c, ++it) {
         const uint32_t buf = it & 1;
+        jn = (uint32_t)chunk_pos(base_i, (int)tl, c);
         const int kg = c * 128 + k;
         // this thread's piece (warp-uniform): the segment that contains concat channel kg
         int ps = -1, pj = 0;
@@ -417,8 +440,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
         int npc = 0;
         for (int s = 0; s < p.in.nseg; ++s) npc += (seg_chunk(s) == c);
         for (int q = 0; q < 2 * npc; ++q) useB ^= 1u << ((jn + q) & 3);
-        jn += 2 * npc;
       }
+      base_i = next_base(base_i, (int)tl);
     }
   }
 
