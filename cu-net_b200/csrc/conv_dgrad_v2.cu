@@ -15,6 +15,7 @@
 //     | 8 epilogue warps; TMEM accumulator double-buffered so the MMAs of item i+1 overlap the epilogue of item i.
 #include "loaders.cuh"
 #include "host_util.h"
+#include <type_traits>
 
 namespace cunet {
 
@@ -81,14 +82,22 @@ __device__ __forceinline__ TileSpan tile_span(const PixGeom& g, int tile, int gr
   return s;
 }
 
+// split != 0 (small problems): one CTA per (tile, chunk) work item instead of one persistent CTA per tile list --
+// a low-resolution op has fewer tiles than SMs, and walking its 2-3 chunks serially tripled the kernel's latency.
 __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __grid_constant__ cunet_conv_dgrad_params p,
-                                                                       int ntiles) {
+                                                                       int ntiles_all, int split) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   D2Tail* tail = reinterpret_cast<D2Tail*>(smem + D2_TAIL_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Cin = concat_cin(p.in);
-  const int nchunk = (Cin + 127) >> 7;
+  const int nchunk_all = (Cin + 127) >> 7;
+  // chunk range [c0, c0 + nchunk) and tile list {tile0, tile0 + tstride, ...} < ntiles of this CTA
+  const int c0 = split ? (int)blockIdx.x % nchunk_all : 0;
+  const int nchunk = split ? 1 : nchunk_all;
+  const int tile0 = split ? (int)blockIdx.x / nchunk_all : (int)blockIdx.x;
+  const int tstride = split ? ntiles_all : (int)gridDim.x;
+  const int ntiles = ntiles_all;
   int grouped = 0;
   for (int s = 0; s < p.in.nseg; ++s) grouped |= p.in.seg[s].up;
   const int nkb = (p.CoutPad + 63) >> 6;  // K blocks of the Cout contraction (1 or 2)
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tail->tmem_base, 256);
-  compute_bn_coefs(p.in, &tail->bn, nchunk * 128, tid, D2_THREADS);
+  compute_bn_coefs(p.in, &tail->bn, nchunk_all * 128, tid, D2_THREADS);
   compute_grad_coefs(p.dy, &tail->gc, tid, D2_THREADS);
   tc_fence_before();
   __syncthreads();
@@ -129,11 +138,14 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
   // one with two pieces (four slots), and landing / transforming the next tile's dT behind it left a ~4 us
   // bubble per tile in the in-kernel timeline (tools/trace_dgrad.py).
   int njc[4] = {0, 0, 0, 0}, prefix[4] = {0, 0, 0, 0};
-  for (int s = 0; s < p.in.nseg; ++s) njc[seg_chunk(s) & 3] += 2;
+  for (int s = 0; s < p.in.nseg; ++s) {
+    const int cl = seg_chunk(s) - c0;  // local chunk index
+    if (cl >= 0 && cl < nchunk) njc[cl & 3] += 2;
+  }
   for (int c = 1; c < 4; ++c) prefix[c] = prefix[c - 1] + njc[c - 1];
   const int NJ = prefix[nchunk - 1] + njc[nchunk - 1];
   const int dTn = 1 + (p.dy.mode == 1 ? 1 : 0) + (p.dy.pooled ? 1 : 0);
-  const int ntile_cta = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int ntile_cta = (tile0 < ntiles) ? (ntiles - 1 - tile0) / tstride + 1 : 0;
   const int early = nchunk >= 2 ? 1 : 0;  // next tile's dT jobs go before the last chunk
   // job index of the dT jobs of the CTA's tile #i+1, given base(i); and base(i+1)
   auto pos_next_dt = [&](int base_i) { return base_i + (early ? NJ - njc[nchunk - 1] : NJ); };
@@ -165,12 +177,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
         if (p.dy.mode == 1) land(reinterpret_cast<const char*>(p.dy.t) + (long)r0 * ldo, (uint32_t)(nr * ldo), false);
         if (p.dy.pooled) land(p.dy.pool_idx + (long)r0 * p.dy.C, (uint32_t)(nr * p.dy.C), false);
       };
-      if (ntile_cta > 0) land_dt(blockIdx.x);
+      if (ntile_cta > 0) land_dt(tile0);
       int i = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      for (int tile = tile0; tile < ntiles; tile += tstride, ++i) {
         const TileSpan sp = tile_span(geom, tile, grouped);
-        for (int c = 0; c < nchunk; ++c) {
-          if (early && c == nchunk - 1 && i + 1 < ntile_cta) land_dt(tile + gridDim.x);
+        for (int cl = 0; cl < nchunk; ++cl) {
+          const int c = c0 + cl;
+          if (early && cl == nchunk - 1 && i + 1 < ntile_cta) land_dt(tile + tstride);
           for (int s = 0; s < p.in.nseg; ++s) {
             if (seg_chunk(s) != c) continue;
             const cunet_seg& sg = p.in.seg[s];
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
                  (p.gacc[s].G && p.gacc[s].accumulate) ? bytes : 0u, true);
           }
         }
-        if (!early && i + 1 < ntile_cta) land_dt(tile + gridDim.x);
+        if (!early && i + 1 < ntile_cta) land_dt(tile + tstride);
       }
     }
   } else if (warp == 1) {
@@ -189,8 +202,9 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     if (lane == 0) {
       uint32_t it = 0;
       const uint32_t wbytes = (uint32_t)nkb * 16384u;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int c = 0; c < nchunk; ++c, ++it) {
+      for (int tile = tile0; tile < ntiles; tile += tstride) {
+        for (int cl = 0; cl < nchunk; ++cl, ++it) {
+          const int c = c0 + cl;
           mbar_wait(&tail->w_free, (it & 1) ^ 1);
           mbar_arrive_expect_tx(&tail->w_full, wbytes);
           bulk_g2s(smem + D2_W_OFF, reinterpret_cast<const char*>(p.wpack_dgrad) + (size_t)c * wbytes, wbytes,
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
       const uint32_t idesc = make_idesc(Elem<bf16>::FMT, 128, 128, 0, 0);
       const uint32_t a_w = smem_u32(smem + D2_W_OFF), b_dt = smem_u32(smem + D2_A_OFF);
       uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      for (int tile = tile0; tile < ntiles; tile += tstride, ++tl) {
         mbar_wait(&tail->dt_ready, tl & 1);
         for (int c = 0; c < nchunk; ++c, ++it) {
           const uint32_t buf = it & 1;
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
       useA ^= 1u << slot;
       ++jn;
     };
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile0; tile < ntiles; tile += tstride, ++tl) {
       // row table of this tile (thread t <-> tile row t)
       {
         int n = 0, h = 0, w = 0;
@@ -315,11 +329,12 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     uint32_t jn = 0, it = 0, tl = 0;
     int base_i = dTn;   // base(0)
     uint32_t useB = 0;  // bit s: parity of the number of party-B jobs seen so far on slot s (every warp counts every job)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile0; tile < ntiles; tile += tstride, ++tl) {
       const TileSpan sp = tile_span(geom, tile, grouped);
-      for (int c = 0; c < nchunk; ++c, ++it) {
+      for (int cl = 0; cl < nchunk; ++cl, ++it) {
+        const int c = c0 + cl;
         const uint32_t buf = it & 1;
-        jn = (uint32_t)chunk_pos(base_i, (int)tl, c);
+        jn = (uint32_t)chunk_pos(base_i, (int)tl, cl);
         const int kg = c * 128 + k;
         // this thread's piece (warp-uniform): the segment that contains concat channel kg
         int ps = -1, pj = 0;
@@ -359,25 +374,50 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
             float v[8];
             tmem_ld8(tmem + buf * 128 + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
             if (!sg.up) {
+              // raster tiles: tile row == block row, validity is a prefix (px < nfull); grouped tiles go through
+              // the row table.  accumulate / gstats are warp-uniform: the four variants are separate loops so the
+              // per-pixel code carries no predicates.
+              auto px_loop = [&](auto ACC, auto GST, auto RASTER) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int rdr = rd[col0 + q];
-                if (rdr < 0) continue;
-                const int off = (rdr - rd0) * Cp + kl;
-                const float x = __bfloat162float(X[off]);
-                const float dz = fmaf(x, sc, sh) > 0.f ? v[q] : 0.f;
-                const float xh = (x - mu) * is;
-                a_db += dz;
-                a_dg += dz * xh;
-                float gv = gm * dz;
-                if (ga.accumulate) gv += __bfloat162float(Gs[off]);
-                const bf16 gb = __float2bfloat16_rn(gv);
-                Gs[off] = gb;
-                if (ga.gstats) {
-                  const float gf = __bfloat162float(gb);
-                  a_g += gf;
-                  a_gt += gf * xh;
+                for (int q = 0; q < 8; ++q) {
+                  int loc;
+                  if (decltype(RASTER)::value) {
+                    loc = col0 + q;
+                    if (loc >= sp.nfull) continue;
+                  } else {
+                    const int rdr = rd[col0 + q];
+                    if (rdr < 0) continue;
+                    loc = rdr - rd0;
+                  }
+                  const int off = loc * Cp + kl;
+                  const float x = __bfloat162float(X[off]);
+                  const float dz = fmaf(x, sc, sh) > 0.f ? v[q] : 0.f;
+                  const float xh = (x - mu) * is;
+                  a_db += dz;
+                  a_dg = fmaf(dz, xh, a_dg);
+                  float gv = gm * dz;
+                  if (decltype(ACC)::value) gv += __bfloat162float(Gs[off]);
+                  const bf16 gb = __float2bfloat16_rn(gv);
+                  Gs[off] = gb;
+                  if (decltype(GST)::value) {
+                    const float gf = __bfloat162float(gb);
+                    a_g += gf;
+                    a_gt = fmaf(gf, xh, a_gt);
+                  }
                 }
+              };
+              using TT = std::true_type;
+              using FF = std::false_type;
+              const int sel = (ga.accumulate ? 1 : 0) | (ga.gstats ? 2 : 0) | (grouped ? 0 : 4);
+              switch (sel) {
+                case 0: px_loop(FF{}, FF{}, FF{}); break;
+                case 1: px_loop(TT{}, FF{}, FF{}); break;
+                case 2: px_loop(FF{}, TT{}, FF{}); break;
+                case 3: px_loop(TT{}, TT{}, FF{}); break;
+                case 4: px_loop(FF{}, FF{}, TT{}); break;
+                case 5: px_loop(TT{}, FF{}, TT{}); break;
+                case 6: px_loop(FF{}, TT{}, TT{}); break;
+                default: px_loop(TT{}, TT{}, TT{}); break;
               }
             } else {
               // upsampled source: columns 4w..4w+3 are the four children of low-resolution pixel w
@@ -495,11 +535,13 @@ int cunet_conv_dgrad_v2_try(const cunet_conv_dgrad_params* p, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const int grid = ntiles < sms ? ntiles : sms;
+  const int nchunk = (cin + 127) / 128;
+  const int split = (ntiles * nchunk <= sms) ? 1 : 0;   // small problem: one CTA per (tile, chunk)
+  const int grid = split ? ntiles * nchunk : (ntiles < sms ? ntiles : sms);
   const size_t smem = D2_TAIL_OFF + sizeof(D2Tail) + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_dgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_dgrad_v2 attr", e);
-  conv_dgrad_v2_kernel<<<grid, D2_THREADS, smem, st>>>(*p, ntiles);
+  conv_dgrad_v2_kernel<<<grid, D2_THREADS, smem, st>>>(*p, ntiles, split);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cunet_fail_cuda("conv_dgrad_v2 launch", e);
   return 1;
