@@ -12,6 +12,7 @@
 // reference-layout gradient with red.global.add.f32 (split-K over pixels across CTAs).
 #include "loaders.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace cunet {
 
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(WG_THREADS, StageGeom<T>::MIN_CTAS) conv_wgrad
 using namespace cunet;
 
 int cunet_conv_wgrad3x3_launch(const cunet_conv_wgrad_params* p, cudaStream_t st);  // conv_wgrad3x3.cu
+int cunet_conv_wgrad_v2_try(const cunet_conv_wgrad_params* p, cudaStream_t st);     // conv_wgrad_v2.cu
 
 extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) {
   if (!p) return cunet_fail("conv_wgrad: null params");
@@ -236,6 +238,13 @@ extern "C" int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream) 
   if (M <= 0) return 0;
   if (p->taps == 9 && cin <= 128 && p->dy.C == 32 && p->dw_cin == 0)   // the network's 3x3: all taps in one CTA
     return cunet_conv_wgrad3x3_launch(p, reinterpret_cast<cudaStream_t>(stream));
+  {
+    static const bool v1_only = getenv("CUNET_WGRAD_V1") != nullptr;
+    if (!v1_only) {
+      const int r = cunet_conv_wgrad_v2_try(p, reinterpret_cast<cudaStream_t>(stream));
+      if (r != 0) return r < 0 ? r : 0;
+    }
+  }
   const int kbe = p->dtype == CUNET_BF16 ? 64 : 32;
   const int R = p->dtype == CUNET_BF16 ? 64 : 32;
   const int npad = ((p->dy.C + kbe - 1) / kbe) * kbe;  // whole MN groups of the gradient operand
