@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
   float* red = reinterpret_cast<float*>(smem + 128 * LD_EP * 4);  // [256][16] partial sums
 
   // thread -> channel quad (32 quads per chunk) x 8 row groups.  Each quad lies inside one segment.
-  float a_db[4] = {0, 0, 0, 0}, a_dg[4] = {0, 0, 0, 0}, a_g[4] = {0, 0, 0, 0}, a_gt[4] = {0, 0, 0, 0};
+  float a_db[4] = {0, 0, 0, 0}, a_dg[4] = {0, 0, 0, 0};
   const int quad = tid & 31;
   const int rg = tid >> 5;  // 0..7 for the epilogue warps
   const int k0 = chunk * 128 + quad * 4;
@@ -284,33 +284,22 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
         for (int e = 0; e < 4; ++e) gv[e] += ov[e];
       }
       store4<T>(G + row * ga.ld + cl, gv);  // gv <- values as stored
-      if (ga.gstats) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          a_g[e] += gv[e];
-          a_gt[e] += gv[e] * (xv[e] - mu[e]) * is[e];
-        }
-      }
     }
   }
   if (warp < 8) {
     float4* rp = reinterpret_cast<float4*>(red + tid * 16);
     rp[0] = make_float4(a_db[0], a_db[1], a_db[2], a_db[3]);
     rp[1] = make_float4(a_dg[0], a_dg[1], a_dg[2], a_dg[3]);
-    rp[2] = make_float4(a_g[0], a_g[1], a_g[2], a_g[3]);
-    rp[3] = make_float4(a_gt[0], a_gt[1], a_gt[2], a_gt[3]);
   }
   __syncthreads();
   if (tid < 128) {
     const int k = chunk * 128 + tid;
     if (k < Cin) {
       const int q = tid >> 2, e = tid & 3;
-      float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      float s0 = 0, s1 = 0;
       for (int t = q; t < 256; t += 32) {
         s0 += red[t * 16 + e];
         s1 += red[t * 16 + 4 + e];
-        s2 += red[t * 16 + 8 + e];
-        s3 += red[t * 16 + 12 + e];
       }
       int si = 0;
       while (k >= tail->bn.seg_start[si + 1]) ++si;
@@ -319,8 +308,11 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
         atomicAdd(p.dgamma + k, s1);
         if (p.gacc[si].gstats) {
           const int cl = k - tail->bn.seg_start[si];
-          atomicAdd(p.gacc[si].gstats + cl, (double)s2);
-          atomicAdd(p.gacc[si].gstats + p.in.seg[si].C + cl, (double)s3);
+          // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma): every consumer of a tensor
+          // normalises it with the same batch statistics (see conv_dgrad_v2.cu)
+          const float gmk = p.in.gamma[k];
+          atomicAdd(p.gacc[si].gstats + cl, (double)(gmk * s0));
+          atomicAdd(p.gacc[si].gstats + p.in.seg[si].C + cl, (double)(gmk * s1));
         }
       }
     }

@@ -26,7 +26,7 @@ __device__ long long* g_d2_trace = nullptr;
     if (trace != nullptr && blockIdx.x == 0) trace[(slot_expr)] = clock64(); \
   } while (0)
 
-constexpr int D2_THREADS = 480;  // 15 warps
+constexpr int D2_THREADS = 512;  // 16 warps
 constexpr int D2_NSLOT = 4;
 constexpr int D2_SLOT = 32768;
 constexpr int D2_A_OFF = D2_NSLOT * D2_SLOT;  // dT operand: 2 K blocks x 16 KB
@@ -39,8 +39,11 @@ struct D2Tail {
   uint64_t slot_fullA[D2_NSLOT], slot_fullB[D2_NSLOT], slot_empty[D2_NSLOT];
   uint64_t dt_ready, dt_free, w_full, w_free;
   uint64_t acc_full[2], acc_free[2];
+  // g_ready[item & 1]: the 8 epilogue warps finished a chunk's G slots.  A warp arrives here BEFORE acc_free, and
+  // item i+2 cannot start before all 8 acc_free arrivals of item i, so the two barriers never see a lapped arrival.
+  uint64_t g_ready[2];
   uint32_t tmem_base;
-  int rows_rd[4][128];
+  alignas(16) int rows_rd[4][128];
   int rows_ru[4][128];
   int rows_pos[4][128];  // position inside the 2x2 window: (h & 1) * 2 + (w & 1)
   BnSmem bn;
@@ -54,6 +57,14 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
                "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ float lds_bf16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return __uint_as_float((uint32_t)v << 16);
+}
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -119,6 +130,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->acc_full[b], 1);
       mbar_init(&tail->acc_free[b], 8);
+      mbar_init(&tail->g_ready[b], 8);
     }
     fence_mbar_init();
   }
@@ -320,12 +332,48 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
       if (lane == 0) mbar_arrive(&tail->dt_ready);
       if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 3);
     }
+  } else if (warp == 15) {
+    // ============================================================== G store issuer
+    // One thread turns every finished chunk into bulk stores and recycles its landing slots, so the epilogue warps
+    // never synchronise with each other or wait for a store (they used to: a 256-thread named barrier plus a
+    // store-read wait of 0.5-0.9 us per chunk on the critical path).
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      int base_i = dTn;
+      for (int tile = tile0; tile < ntiles; tile += tstride, ++tl) {
+        const TileSpan sp = tile_span(geom, tile, grouped);
+        for (int cl = 0; cl < nchunk; ++cl, ++it) {
+          const int c = c0 + cl;
+          const uint32_t jn = (uint32_t)chunk_pos(base_i, (int)tl, cl);
+          mbar_wait(&tail->g_ready[it & 1], (it >> 1) & 1);
+          if (it < 24) D2_TRACE(64 + it * 8 + 4);
+          int j = 0;
+          for (int s = 0; s < p.in.nseg; ++s) {
+            if (seg_chunk(s) != c) continue;
+            const cunet_seg& sg = p.in.seg[s];
+            const uint32_t jgs = jn + 2 * j + 1;
+            if (p.gacc[s].G != nullptr) {
+              const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
+              bulk_s2g(reinterpret_cast<char*>(p.gacc[s].G) + (long)x0 * sg.C * 2, smem + (jgs & 3) * D2_SLOT,
+                       (uint32_t)(nx * sg.C * 2));
+            }
+            ++j;
+          }
+          bulk_commit();
+          bulk_wait_read0();  // the slots may be overwritten once the stores have read them
+          if (it < 24) D2_TRACE(64 + it * 8 + 5);
+          for (int q = 0; q < 2 * j; ++q) mbar_arrive(&tail->slot_empty[(jn + q) & 3]);
+        }
+        base_i = next_base(base_i, (int)tl);
+      }
+    }
   } else {
     // ============================================================== epilogue (warps 7-14, 256 threads)
     const int e = warp - 7;
     const int qd = warp & 3, hf = e >> 2;  // TMEM lane quarter (hardware: warp % 4), pixel-column half
     const int k = qd * 32 + lane;          // channel within the chunk
     const int et = tid - 224;              // 0..255
+    const int lw = 31 - __clz(p.W), whm = (p.W >> 1) - 1;  // grouped tiles only exist for power-of-two W
     uint32_t jn = 0, it = 0, tl = 0;
     int base_i = dTn;   // base(0)
     uint32_t useB = 0;  // bit s: parity of the number of party-B jobs seen so far on slot s (every warp counts every job)
@@ -347,7 +395,6 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
           }
         }
         const uint32_t jx = jn + 2 * pj, jg = jx + 1;
-        float a_db = 0.f, a_dg = 0.f, a_g = 0.f, a_gt = 0.f;
         if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 0);
         mbar_wait(&tail->acc_full[buf], (it >> 1) & 1);
         tc_fence_after();
@@ -360,122 +407,114 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
           mbar_wait(&tail->slot_fullB[jx & 3], (useB >> (jx & 3)) & 1);
           mbar_wait(&tail->slot_fullB[jg & 3], (useB >> (jg & 3)) & 1);
           if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 2);
-          const bf16* X = reinterpret_cast<const bf16*>(smem + (jx & 3) * D2_SLOT);
-          bf16* Gs = reinterpret_cast<bf16*>(smem + (jg & 3) * D2_SLOT);
           const int kl = kg - tail->bn.seg_start[ps];
-          const int Cp = sg.C;
-          const float sc = tail->bn.scale[kg], sh = tail->bn.shift[kg], mu = tail->bn.mean[kg], is = tail->bn.istd[kg];
+          const int Cp = sg.C, Cp2 = Cp * 2;
+          // shared-window addresses of this thread's channel in the x slot; the G slot sits gdelta bytes away
+          const uint32_t xa = smem_u32(smem + (jx & 3) * D2_SLOT) + (uint32_t)(kl * 2);
+          const uint32_t gdelta = (uint32_t)(((int)(jg & 3) - (int)(jx & 3)) * D2_SLOT);
+          const float sc = tail->bn.scale[kg], sh = tail->bn.shift[kg], is = tail->bn.istd[kg];
+          const float nmi = -tail->bn.mean[kg] * is;  // xhat = x * istd - mean * istd
           const float gm = p.in.gamma[kg];
-          const int* rd = tail->rows_rd[tl & 3];
-          const int* ru = tail->rows_ru[tl & 3];
-          const int rd0 = rd[0], ru0 = ru[0];
-          for (int g8 = 0; g8 < 8; ++g8) {
-            const int col0 = hf * 64 + g8 * 8;
-            float v[8];
-            tmem_ld8(tmem + buf * 128 + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
-            if (!sg.up) {
-              // raster tiles: tile row == block row, validity is a prefix (px < nfull); grouped tiles go through
-              // the row table.  accumulate / gstats are warp-uniform: the four variants are separate loops so the
-              // per-pixel code carries no predicates.
-              auto px_loop = [&](auto ACC, auto GST, auto RASTER) {
+          float a_db = 0.f, a_dg = 0.f;
+          const uint32_t tbase = tmem + buf * 128 + ((uint32_t)(qd * 32) << 16);
+          if (!sg.up) {
+            // Tile column t <-> pixel: raster tiles t; grouped tiles window t>>2 (row-major over the half-resolution
+            // image rows, 2W*(wi / Wh) + 2*(wi % Wh) pixels from the tile's first row) plus {0, 1, W, W+1}[t & 3].
+            // Valid columns are a prefix (t < nfull) in both orders, so no row table is read here.
+            const uint32_t o1 = (uint32_t)Cp2, o2 = (uint32_t)((grouped ? p.W : 2) * Cp2),
+                           o3 = (uint32_t)((grouped ? p.W + 1 : 3) * Cp2);
+            auto batch = [&](auto ACC, auto FULL, const float* v, uint32_t aA, uint32_t aB, int nval) {
+              // staged: all loads, then the arithmetic, then all stores (independent chains for the scheduler)
+              uint32_t ad[8];
+              ad[0] = aA; ad[1] = aA + o1; ad[2] = aA + o2; ad[3] = aA + o3;
+              ad[4] = aB; ad[5] = aB + o1; ad[6] = aB + o2; ad[7] = aB + o3;
+              float x[8], go[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  int loc;
-                  if (decltype(RASTER)::value) {
-                    loc = col0 + q;
-                    if (loc >= sp.nfull) continue;
-                  } else {
-                    const int rdr = rd[col0 + q];
-                    if (rdr < 0) continue;
-                    loc = rdr - rd0;
-                  }
-                  const int off = loc * Cp + kl;
-                  const float x = __bfloat162float(X[off]);
-                  const float dz = fmaf(x, sc, sh) > 0.f ? v[q] : 0.f;
-                  const float xh = (x - mu) * is;
-                  a_db += dz;
-                  a_dg = fmaf(dz, xh, a_dg);
-                  float gv = gm * dz;
-                  if (decltype(ACC)::value) gv += __bfloat162float(Gs[off]);
-                  const bf16 gb = __float2bfloat16_rn(gv);
-                  Gs[off] = gb;
-                  if (decltype(GST)::value) {
-                    const float gf = __bfloat162float(gb);
-                    a_g += gf;
-                    a_gt = fmaf(gf, xh, a_gt);
-                  }
-                }
-              };
-              using TT = std::true_type;
-              using FF = std::false_type;
-              const int sel = (ga.accumulate ? 1 : 0) | (ga.gstats ? 2 : 0) | (grouped ? 0 : 4);
-              switch (sel) {
-                case 0: px_loop(FF{}, FF{}, FF{}); break;
-                case 1: px_loop(TT{}, FF{}, FF{}); break;
-                case 2: px_loop(FF{}, TT{}, FF{}); break;
-                case 3: px_loop(TT{}, TT{}, FF{}); break;
-                case 4: px_loop(FF{}, FF{}, TT{}); break;
-                case 5: px_loop(TT{}, FF{}, TT{}); break;
-                case 6: px_loop(FF{}, TT{}, TT{}); break;
-                default: px_loop(TT{}, TT{}, TT{}); break;
+              for (int q = 0; q < 8; ++q) x[q] = (decltype(FULL)::value || q < nval) ? lds_bf16(ad[q]) : 0.f;
+              if (decltype(ACC)::value) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) go[q] = (decltype(FULL)::value || q < nval) ? lds_bf16(ad[q] + gdelta) : 0.f;
               }
-            } else {
-              // upsampled source: columns 4w..4w+3 are the four children of low-resolution pixel w
+              uint16_t gb[8];
 #pragma unroll
-              for (int wq = 0; wq < 2; ++wq) {
-                if (rd[col0 + 4 * wq] < 0) continue;
-                const int off = (ru[col0 + 4 * wq] - ru0) * Cp + kl;
-                const float x = __bfloat162float(X[off]);
-                const float xh = (x - mu) * is;
-                const bool on = fmaf(x, sc, sh) > 0.f;
-                float dzs = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) dzs += on ? v[4 * wq + ch] : 0.f;
-                a_db += dzs;
-                a_dg += dzs * xh;
-                float gv = gm * dzs;
-                if (ga.accumulate) gv += __bfloat162float(Gs[off]);
-                const bf16 gb = __float2bfloat16_rn(gv);
-                Gs[off] = gb;
-                if (ga.gstats) {
-                  const float gf = __bfloat162float(gb);
-                  a_g += gf;
-                  a_gt += gf * xh;
-                }
+              for (int q = 0; q < 8; ++q) {
+                const bool on = fmaf(x[q], sc, sh) > 0.f && (decltype(FULL)::value || q < nval);
+                const float dz = on ? v[q] : 0.f;
+                a_db += dz;
+                a_dg = fmaf(dz, fmaf(x[q], is, nmi), a_dg);
+                const float gv = decltype(ACC)::value ? fmaf(gm, dz, go[q]) : gm * dz;
+                gb[q] = __bfloat16_as_ushort(__float2bfloat16_rn(gv));
               }
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (decltype(FULL)::value || q < nval) sts_u16(ad[q] + gdelta, gb[q]);
+            };
+            using TT = std::true_type;
+            using FF = std::false_type;
+            for (int g8 = 0; g8 < 8; ++g8) {
+              const int col0 = hf * 64 + g8 * 8;
+              const int nval = sp.nfull - col0;
+              if (nval <= 0) break;
+              float v[8];
+              tmem_ld8(tbase + (uint32_t)col0, v);
+              int pa, pb;
+              if (grouped) {
+                const int wa = col0 >> 2, wb = wa + 1;
+                pa = (((wa >> (lw - 1)) << 1) << lw) + ((wa & whm) << 1);
+                pb = (((wb >> (lw - 1)) << 1) << lw) + ((wb & whm) << 1);
+              } else {
+                pa = col0;
+                pb = col0 + 4;
+              }
+              const uint32_t aA = xa + (uint32_t)(pa * Cp2), aB = xa + (uint32_t)(pb * Cp2);
+              if (nval >= 8) {
+                if (ga.accumulate) batch(TT{}, TT{}, v, aA, aB, 8);
+                else batch(FF{}, TT{}, v, aA, aB, 8);
+              } else {
+                if (ga.accumulate) batch(TT{}, FF{}, v, aA, aB, nval);
+                else batch(FF{}, FF{}, v, aA, aB, nval);
+              }
+            }
+          } else {
+            // upsampled source: columns 4w..4w+3 are the four children of half-resolution pixel low0 + w
+            for (int g8 = 0; g8 < 8; ++g8) {
+              const int col0 = hf * 64 + g8 * 8;
+              if (col0 >= sp.nfull) break;
+              float v[8];
+              tmem_ld8(tbase + (uint32_t)col0, v);
+              const uint32_t a0 = xa + (uint32_t)((col0 >> 2) * Cp2);
+              const bool ok1 = col0 + 4 < sp.nfull;
+              const float x0 = lds_bf16(a0), x1 = ok1 ? lds_bf16(a0 + Cp2) : 0.f;
+              float g0 = 0.f, g1 = 0.f;
+              if (ga.accumulate) {
+                g0 = lds_bf16(a0 + gdelta);
+                g1 = ok1 ? lds_bf16(a0 + Cp2 + gdelta) : 0.f;
+              }
+              const float d0 = fmaf(x0, sc, sh) > 0.f ? (v[0] + v[1]) + (v[2] + v[3]) : 0.f;
+              const float d1 = (ok1 && fmaf(x1, sc, sh) > 0.f) ? (v[4] + v[5]) + (v[6] + v[7]) : 0.f;
+              a_db += d0 + d1;
+              a_dg = fmaf(d0, fmaf(x0, is, nmi), a_dg);
+              a_dg = fmaf(d1, fmaf(x1, is, nmi), a_dg);
+              sts_u16(a0 + gdelta, __bfloat16_as_ushort(__float2bfloat16_rn(fmaf(gm, d0, g0))));
+              if (ok1) sts_u16(a0 + Cp2 + gdelta, __bfloat16_as_ushort(__float2bfloat16_rn(fmaf(gm, d1, g1))));
             }
           }
           atomicAdd(p.dbeta + kg, a_db);
           atomicAdd(p.dgamma + kg, a_dg);
           if (ga.gstats) {
-            atomicAdd(ga.gstats + kl, (double)a_g);
-            atomicAdd(ga.gstats + Cp + kl, (double)a_gt);
+            // this consumer's share of (sum G, sum G*xhat): G = sum_consumers gamma*dz and every consumer of a
+            // tensor normalises it with the same batch statistics, so the sums are gamma * (dbeta, dgamma)
+            atomicAdd(ga.gstats + kl, (double)(gm * a_db));
+            atomicAdd(ga.gstats + Cp + kl, (double)(gm * a_dg));
           }
         }
         if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 3);
+        fence_proxy_async();  // G slot writes -> visible to the bulk store
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->acc_free[buf]);  // TMEM buffer drained by this warp
-        fence_proxy_async();
-        named_bar_sync(2, 256);  // every G slot of this chunk is final
-        if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 4);
-        if (et == 0) {
-          int j = 0;
-          for (int s = 0; s < p.in.nseg; ++s) {
-            if (seg_chunk(s) != c) continue;
-            const cunet_seg& sg = p.in.seg[s];
-            const uint32_t jgs = jn + 2 * j + 1;
-            if (p.gacc[s].G != nullptr) {
-              const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
-              bulk_s2g(reinterpret_cast<char*>(p.gacc[s].G) + (long)x0 * sg.C * 2, smem + (jgs & 3) * D2_SLOT,
-                       (uint32_t)(nx * sg.C * 2));
-            }
-            ++j;
-          }
-          bulk_commit();
-          bulk_wait_read0();  // the slots may be overwritten once the stores have read them
-          if (it < 24) D2_TRACE(64 + it * 8 + 5);
-          for (int q = 0; q < 2 * j; ++q) mbar_arrive(&tail->slot_empty[(jn + q) & 3]);
+        if (lane == 0) {
+          mbar_arrive(&tail->g_ready[it & 1]);   // before acc_free: nobody can lap this barrier (see D2Tail)
+          mbar_arrive(&tail->acc_free[buf]);     // TMEM buffer drained by this warp
         }
         int npc = 0;
         for (int s = 0; s < p.in.nseg; ++s) npc += (seg_chunk(s) == c);

@@ -154,6 +154,31 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
     const bool gcol_ok = cc * 8 < p.dy.C;
     const bool gcol_used = cc * 8 < npad;
     uint32_t jn = 0, ai = 0, si = 0;
+    // per-chunk constants of this thread's 16-byte column, hoisted out of the stage loop (the per-chunk segment
+    // search and coefficient loads used to cost more instructions than the four transform passes they served)
+    ActCoef<bf16> acf[3];
+    int cs_s[3], cs_lo[3], cs_hi[3], cs_cl2[3], cs_ldx[3], cs_up[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int ch = c * 128 + cc * 8;
+      acf[c].load(&tail->bn, ch < MAX_CIN ? ch : 0);
+      cs_s[c] = -1; cs_lo[c] = p.in.nseg; cs_hi[c] = -1; cs_cl2[c] = 0; cs_ldx[c] = 0; cs_up[c] = 0;
+      if (c < nchunk) {
+        if (ch < Cin) {
+          int s = 0;
+          while (ch >= tail->bn.seg_start[s + 1]) ++s;
+          cs_s[c] = s;
+          cs_cl2[c] = (ch - tail->bn.seg_start[s]) * 2;
+          cs_ldx[c] = p.in.seg[s].C * 2;
+          cs_up[c] = p.in.seg[s].up;
+        }
+        for (int q = 0; q < p.in.nseg; ++q)
+          if ((tail->bn.seg_start[q] >> 7) == c) {
+            cs_lo[c] = min(cs_lo[c], q);
+            cs_hi[c] = max(cs_hi[c], q);
+          }
+      }
+    }
     for (int st = st0; st < st1; ++st, ++si) {
       const int m0 = st * W2_R, nv = min(W2_R, M - m0);
       const uint32_t par = si & 1;
@@ -215,38 +240,24 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
       }
       jn += dTn;
       // ---- activation operand per chunk -> A ring
-      for (int c = 0; c < nchunk; ++c, ++ai) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c >= nchunk) break;
         const uint32_t ab = ai % 3;
-        const int ch = c * 128 + cc * 8;
-        // the segment (landing job) that holds concat channel ch
-        int s = -1;
-        if (ch < Cin) {
-          s = 0;
-          while (ch >= tail->bn.seg_start[s + 1]) ++s;
-        }
+        const int s = cs_s[c], s_lo = cs_lo[c], s_hi = cs_hi[c];
         // every warp must observe every segment job of this chunk (single-party ring discipline)
-        int s_lo = p.in.nseg, s_hi = -1;
-        for (int q = 0; q < p.in.nseg; ++q)
-          if ((tail->bn.seg_start[q] >> 7) == c) {
-            s_lo = min(s_lo, q);
-            s_hi = max(s_hi, q);
-          }
         for (int q = s_lo; q <= s_hi; ++q) mbar_wait(&tail->slot_full[(jn + q) & 7], ((jn + q) >> 3) & 1);
         mbar_wait(&tail->a_free[ab], ((ai / 3) & 1) ^ 1);
         const uint32_t abase = smem_u32(smem + W2_A_OFF + ab * 16384);
-        ActCoef<bf16> acf;
-        acf.load(&tail->bn, ch < MAX_CIN ? ch : 0);
-        const cunet_seg& sg = p.in.seg[s < 0 ? 0 : s];
-        const uint8_t* rx = smem + ((jn + (s < 0 ? 0 : s)) & 7) * W2_SLOT;
-        const int cl2 = s < 0 ? 0 : (ch - tail->bn.seg_start[s]) * 2;
-        const int ldx = sg.C * 2;
+        const uint8_t* rx = smem + ((jn + (s < 0 ? 0 : s)) & 7) * W2_SLOT + cs_cl2[c];
+        const int ldx = cs_ldx[c];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = rb + 16 * q;
           uint4 o = make_uint4(0, 0, 0, 0), lo;
           if (s >= 0 && r < nv) {
-            const int loc = sg.up ? lowloc[r] : r;
-            o = acf.apply(*reinterpret_cast<const uint4*>(rx + loc * ldx + cl2), lo);
+            const int loc = cs_up[c] ? lowloc[r] : r;
+            o = acf[c].apply(*reinterpret_cast<const uint4*>(rx + loc * ldx), lo);
           }
           sts128(abase + (cc >> 3) * W2_SUB + tile_off_mn<bf16>(r, cc & 7), o);
         }
@@ -256,6 +267,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
           mbar_arrive(&tail->a_full[ab]);
           for (int q = s_lo; q <= s_hi; ++q) mbar_arrive(&tail->slot_empty[(jn + q) & 7]);
         }
+        ++ai;
       }
       jn += p.in.nseg;
     }

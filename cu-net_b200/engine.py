@@ -280,7 +280,7 @@ class Engine(object):
             self._concat(dp.inp, op, 1)
             for i, ((t, up), (acc, last)) in enumerate(zip(op.srcs, flags)):
                 dp.gacc[i].G = self.G[t.name].data_ptr()
-                dp.gacc[i].gstats = self._gstats(t.name) if last else None
+                dp.gacc[i].gstats = self._gstats(t.name)   # every consumer adds its share gamma*(dbeta, dgamma)
                 dp.gacc[i].ld, dp.gacc[i].accumulate = t.C, int(acc)
             self._grad_src(dp.dy, op.out, op)
             dp.N, dp.H, dp.W, dp.taps = N, op.res, op.res, op.taps

@@ -100,7 +100,8 @@ typedef struct {
 /* Per-source accumulator written by a consumer's dgrad epilogue. */
 typedef struct {
   void* G;        /* [rows][ld] dtype; NULL: this source needs no gradient  */
-  double* gstats; /* non-NULL: this is the last consumer -> accumulate (sum G, sum G*xhat) of the final G */
+  double* gstats; /* non-NULL: add this consumer's share of (sum G, sum G*xhat) = gamma*(dbeta, dgamma); every
+                     consumer of the tensor passes it, the buffer is zeroed once per backward pass          */
   int ld;
   int accumulate; /* 0: first consumer in backward order (write), 1: read-modify-write */
 } cunet_gacc;
