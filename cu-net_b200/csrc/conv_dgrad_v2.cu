@@ -27,16 +27,22 @@ __device__ long long* g_d2_trace = nullptr;
   } while (0)
 
 constexpr int D2_THREADS = 512;  // 16 warps
-constexpr int D2_NSLOT = 4;
-constexpr int D2_SLOT = 32768;
-constexpr int D2_A_OFF = D2_NSLOT * D2_SLOT;  // dT operand: 2 K blocks x 16 KB
+// Landing area: a ring of 16 units of 8 KB.  A landing job takes 1-4 contiguous units (a 32-channel piece of a
+// 128-pixel tile is 8 KB, a 128-channel one 32 KB); with four fixed 32 KB slots the small pieces wasted 3/4 of a
+// slot and a tile needed 2.5 ring turns, each a serial free -> land -> compute -> store chain (~4.5 us).
+constexpr int D2_NJOB = 16;      // job-indexed barriers (job j uses index j % 16)
+constexpr int D2_NUNIT = 16;
+constexpr int D2_UNIT = 8192;
+constexpr int D2_A_OFF = D2_NUNIT * D2_UNIT;  // dT operand: 2 K blocks x 16 KB
 constexpr int D2_W_OFF = D2_A_OFF + 32768;    // weight chunk: 2 K blocks x 16 KB
 constexpr int D2_TAIL_OFF = D2_W_OFF + 32768;
 
 struct D2Tail {
   // full barriers are per consumer party (A = dT transformers, B = epilogue): a party only ever sees the phases of
   // its own jobs, so a 1-bit parity wait can never alias a phase completed for the other party
-  uint64_t slot_fullA[D2_NSLOT], slot_fullB[D2_NSLOT], slot_empty[D2_NSLOT];
+  uint64_t job_fullA[D2_NJOB], job_fullB[D2_NJOB], job_empty[D2_NJOB];
+  int job_unit[D2_NJOB];  // first unit of job j's landing area; written by the producer before the copy is armed
+  int job_abs[D2_NJOB];   // producer-private: absolute (unwrapped) unit position of the job
   uint64_t dt_ready, dt_free, w_full, w_free;
   uint64_t acc_full[2], acc_free[2];
   // g_ready[item & 1]: the 8 epilogue warps finished a chunk's G slots.  A warp arrives here BEFORE acc_free, and
@@ -65,6 +71,12 @@ __device__ __forceinline__ float lds_bf16(uint32_t saddr) {
 }
 __device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
+// G += staged increment, performed by the L2 (no read-modify-write through the SM: the old G is never landed)
+__device__ __forceinline__ void bulk_red_add_bf16(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -118,10 +130,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
   long long* trace = g_d2_trace;
 
   if (tid == 0) {
-    for (int s = 0; s < D2_NSLOT; ++s) {
-      mbar_init(&tail->slot_fullA[s], 1);
-      mbar_init(&tail->slot_fullB[s], 1);
-      mbar_init(&tail->slot_empty[s], 1);
+    for (int s = 0; s < D2_NJOB; ++s) {
+      mbar_init(&tail->job_fullA[s], 1);
+      mbar_init(&tail->job_fullB[s], 1);
+      mbar_init(&tail->job_empty[s], 1);
     }
     mbar_init(&tail->dt_ready, 4);
     mbar_init(&tail->dt_free, 1);
@@ -169,14 +181,29 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
   if (warp == 0) {
     // ============================================================== landing producer
     if (lane == 0) {
-      uint32_t jn = 0;
-      auto land = [&](const void* src, uint32_t bytes, bool party_b) {
-        const int slot = jn & 3;
-        uint64_t* full = party_b ? &tail->slot_fullB[slot] : &tail->slot_fullA[slot];
-        mbar_wait(&tail->slot_empty[slot], ((jn >> 2) & 1) ^ 1);
-        if (bytes) {
-          mbar_arrive_expect_tx(full, bytes);
-          bulk_g2s(smem + slot * D2_SLOT, src, bytes, full);
+      uint32_t jn = 0, jh = 0;  // next job, oldest job not yet known to be released
+      int pos = 0;              // absolute unit cursor of the landing ring
+      // size_bytes: extent of the job's area (a G area is also the staging buffer of the outgoing G even when
+      // nothing is loaded into it); load_bytes: what the bulk copy brings in (0 = just publish the area)
+      auto land = [&](const void* src, uint32_t load_bytes, uint32_t size_bytes, bool party_b) {
+        int u = (int)((size_bytes + D2_UNIT - 1) / D2_UNIT);
+        u = u < 1 ? 1 : u;
+        if ((pos & (D2_NUNIT - 1)) + u > D2_NUNIT) pos = (pos + D2_NUNIT - 1) & ~(D2_NUNIT - 1);  // no wrap inside a job
+        // the units [pos, pos+u) were last used one lap ago by jobs that start below pos+u-16: wait for their
+        // release (jobs are released out of order across parties, but waiting in job order is always sufficient)
+        while (jh < jn && (tail->job_abs[jh & (D2_NJOB - 1)] < pos + u - D2_NUNIT || jn - jh >= (uint32_t)D2_NJOB)) {
+          mbar_wait(&tail->job_empty[jh & (D2_NJOB - 1)], (jh / D2_NJOB) & 1);
+          ++jh;
+        }
+        const int ji = jn & (D2_NJOB - 1);
+        const int a = pos & (D2_NUNIT - 1);
+        tail->job_unit[ji] = a;
+        tail->job_abs[ji] = pos;
+        pos += u;
+        uint64_t* full = party_b ? &tail->job_fullB[ji] : &tail->job_fullA[ji];
+        if (load_bytes) {
+          mbar_arrive_expect_tx(full, load_bytes);
+          bulk_g2s(smem + a * D2_UNIT, src, load_bytes, full);
         } else {
           mbar_arrive(full);
         }
@@ -185,9 +212,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
       auto land_dt = [&](int tile) {
         const TileSpan sp = tile_span(geom, tile, grouped);
         const int r0 = p.dy.pooled ? sp.low0 : sp.full0, nr = p.dy.pooled ? sp.nlow : sp.nfull;
-        land(reinterpret_cast<const char*>(p.dy.g) + (long)r0 * ldo, (uint32_t)(nr * ldo), false);
-        if (p.dy.mode == 1) land(reinterpret_cast<const char*>(p.dy.t) + (long)r0 * ldo, (uint32_t)(nr * ldo), false);
-        if (p.dy.pooled) land(p.dy.pool_idx + (long)r0 * p.dy.C, (uint32_t)(nr * p.dy.C), false);
+        const uint32_t gb = (uint32_t)(nr * ldo), ib = (uint32_t)(nr * p.dy.C);
+        land(reinterpret_cast<const char*>(p.dy.g) + (long)r0 * ldo, gb, gb, false);
+        if (p.dy.mode == 1) land(reinterpret_cast<const char*>(p.dy.t) + (long)r0 * ldo, gb, gb, false);
+        if (p.dy.pooled) land(p.dy.pool_idx + (long)r0 * p.dy.C, ib, ib, false);
       };
       if (ntile_cta > 0) land_dt(tile0);
       int i = 0;
@@ -201,9 +229,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
             const cunet_seg& sg = p.in.seg[s];
             const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
             const uint32_t bytes = (uint32_t)(nx * sg.C * 2);
-            land(reinterpret_cast<const char*>(sg.ptr) + (long)x0 * sg.C * 2, p.gacc[s].G ? bytes : 0u, true);
-            land(reinterpret_cast<const char*>(p.gacc[s].G) + (long)x0 * sg.C * 2,
-                 (p.gacc[s].G && p.gacc[s].accumulate) ? bytes : 0u, true);
+            land(reinterpret_cast<const char*>(sg.ptr) + (long)x0 * sg.C * 2, p.gacc[s].G ? bytes : 0u, bytes, true);
+            land(nullptr, 0u, bytes, true);  // staging area of the outgoing G increment (nothing to load)
           }
         }
         if (!early && i + 1 < ntile_cta) land_dt(tile + tstride);
@@ -263,7 +290,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     int base_i = dTn;   // base(0)
     uint32_t useA = 0;  // bit s: parity of the number of party-A jobs seen so far on slot s
     auto next_a = [&](int& slot, uint32_t& ph) {
-      slot = jn & 3;
+      slot = jn & (D2_NJOB - 1);
       ph = (useA >> slot) & 1;
       useA ^= 1u << slot;
       ++jn;
@@ -285,16 +312,16 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
       jn = (uint32_t)pos_next_dt(base_i);          // where the next tile's dT jobs will be
       base_i = next_base(base_i, (int)tl);
       if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 0);
-      mbar_wait(&tail->slot_fullA[sg_slot], sg_ph);
-      if (p.dy.mode == 1) mbar_wait(&tail->slot_fullA[st_slot], st_ph);
-      if (p.dy.pooled) mbar_wait(&tail->slot_fullA[si_slot], si_ph);
+      mbar_wait(&tail->job_fullA[sg_slot], sg_ph);
+      if (p.dy.mode == 1) mbar_wait(&tail->job_fullA[st_slot], st_ph);
+      if (p.dy.pooled) mbar_wait(&tail->job_fullA[si_slot], si_ph);
       if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 1);
       mbar_wait(&tail->dt_free, (tl & 1) ^ 1);  // MMAs of the previous tile no longer read the operand buffer
       if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 2);
       named_bar_sync(1, 128);                   // row table complete
-      const uint8_t* rg = smem + sg_slot * D2_SLOT;
-      const uint8_t* rt = smem + st_slot * D2_SLOT;
-      const uint8_t* ri = smem + si_slot * D2_SLOT;
+      const uint8_t* rg = smem + tail->job_unit[sg_slot] * D2_UNIT;
+      const uint8_t* rt = smem + tail->job_unit[st_slot] * D2_UNIT;
+      const uint8_t* ri = smem + tail->job_unit[si_slot] * D2_UNIT;
       const int* rd = tail->rows_rd[tl & 3];
       const int* ru = tail->rows_ru[tl & 3];
       const int* rpos = tail->rows_pos[tl & 3];
@@ -325,9 +352,9 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
       fence_proxy_async();
       named_bar_sync(1, 128);
       if (t == 0) {  // landing slots of G_out / T_out / idx are free again
-        mbar_arrive(&tail->slot_empty[sg_slot]);
-        if (p.dy.mode == 1) mbar_arrive(&tail->slot_empty[st_slot]);
-        if (p.dy.pooled) mbar_arrive(&tail->slot_empty[si_slot]);
+        mbar_arrive(&tail->job_empty[sg_slot]);
+        if (p.dy.mode == 1) mbar_arrive(&tail->job_empty[st_slot]);
+        if (p.dy.pooled) mbar_arrive(&tail->job_empty[si_slot]);
       }
       if (lane == 0) mbar_arrive(&tail->dt_ready);
       if (t == 0 && tl < 8) D2_TRACE(tl * 8 + 3);
@@ -352,17 +379,20 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
             if (seg_chunk(s) != c) continue;
             const cunet_seg& sg = p.in.seg[s];
             const uint32_t jgs = jn + 2 * j + 1;
+            mbar_arrive(&tail->job_empty[(jn + 2 * j) & (D2_NJOB - 1)]);  // the x area is free right away
             if (p.gacc[s].G != nullptr) {
               const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
-              bulk_s2g(reinterpret_cast<char*>(p.gacc[s].G) + (long)x0 * sg.C * 2, smem + (jgs & 3) * D2_SLOT,
-                       (uint32_t)(nx * sg.C * 2));
+              char* dst = reinterpret_cast<char*>(p.gacc[s].G) + (long)x0 * sg.C * 2;
+              const uint8_t* src = smem + tail->job_unit[jgs & (D2_NJOB - 1)] * D2_UNIT;
+              if (p.gacc[s].accumulate) bulk_red_add_bf16(dst, src, (uint32_t)(nx * sg.C * 2));
+              else bulk_s2g(dst, src, (uint32_t)(nx * sg.C * 2));
             }
             ++j;
           }
           bulk_commit();
-          bulk_wait_read0();  // the slots may be overwritten once the stores have read them
+          bulk_wait_read0();  // the staging areas may be overwritten once the stores have read them
           if (it < 24) D2_TRACE(64 + it * 8 + 5);
-          for (int q = 0; q < 2 * j; ++q) mbar_arrive(&tail->slot_empty[(jn + q) & 3]);
+          for (int q = 0; q < j; ++q) mbar_arrive(&tail->job_empty[(jn + 2 * q + 1) & (D2_NJOB - 1)]);
         }
         base_i = next_base(base_i, (int)tl);
       }
@@ -404,14 +434,16 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
           const cunet_gacc& ga = p.gacc[ps];
           // parity = number of party-B jobs that used the slot before this one (pieces before pj in this chunk
           // occupy other slots: a chunk has at most two pieces = four distinct slots)
-          mbar_wait(&tail->slot_fullB[jx & 3], (useB >> (jx & 3)) & 1);
-          mbar_wait(&tail->slot_fullB[jg & 3], (useB >> (jg & 3)) & 1);
+          const uint32_t ix = jx & (D2_NJOB - 1), ig = jg & (D2_NJOB - 1);
+          mbar_wait(&tail->job_fullB[ix], (useB >> ix) & 1);
+          mbar_wait(&tail->job_fullB[ig], (useB >> ig) & 1);
           if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 2);
           const int kl = kg - tail->bn.seg_start[ps];
           const int Cp = sg.C, Cp2 = Cp * 2;
           // shared-window addresses of this thread's channel in the x slot; the G slot sits gdelta bytes away
-          const uint32_t xa = smem_u32(smem + (jx & 3) * D2_SLOT) + (uint32_t)(kl * 2);
-          const uint32_t gdelta = (uint32_t)(((int)(jg & 3) - (int)(jx & 3)) * D2_SLOT);
+          const int ux = tail->job_unit[ix], ug = tail->job_unit[ig];
+          const uint32_t xa = smem_u32(smem + ux * D2_UNIT) + (uint32_t)(kl * 2);
+          const uint32_t gdelta = (uint32_t)((ug - ux) * D2_UNIT);
           const float sc = tail->bn.scale[kg], sh = tail->bn.shift[kg], is = tail->bn.istd[kg];
           const float nmi = -tail->bn.mean[kg] * is;  // xhat = x * istd - mean * istd
           const float gm = p.in.gamma[kg];
@@ -423,18 +455,14 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
             // Valid columns are a prefix (t < nfull) in both orders, so no row table is read here.
             const uint32_t o1 = (uint32_t)Cp2, o2 = (uint32_t)((grouped ? p.W : 2) * Cp2),
                            o3 = (uint32_t)((grouped ? p.W + 1 : 3) * Cp2);
-            auto batch = [&](auto ACC, auto FULL, const float* v, uint32_t aA, uint32_t aB, int nval) {
+            auto batch = [&](auto FULL, const float* v, uint32_t aA, uint32_t aB, int nval) {
               // staged: all loads, then the arithmetic, then all stores (independent chains for the scheduler)
               uint32_t ad[8];
               ad[0] = aA; ad[1] = aA + o1; ad[2] = aA + o2; ad[3] = aA + o3;
               ad[4] = aB; ad[5] = aB + o1; ad[6] = aB + o2; ad[7] = aB + o3;
-              float x[8], go[8];
+              float x[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) x[q] = (decltype(FULL)::value || q < nval) ? lds_bf16(ad[q]) : 0.f;
-              if (decltype(ACC)::value) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) go[q] = (decltype(FULL)::value || q < nval) ? lds_bf16(ad[q] + gdelta) : 0.f;
-              }
               uint16_t gb[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -442,8 +470,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
                 const float dz = on ? v[q] : 0.f;
                 a_db += dz;
                 a_dg = fmaf(dz, fmaf(x[q], is, nmi), a_dg);
-                const float gv = decltype(ACC)::value ? fmaf(gm, dz, go[q]) : gm * dz;
-                gb[q] = __bfloat16_as_ushort(__float2bfloat16_rn(gv));
+                gb[q] = __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz));
               }
 #pragma unroll
               for (int q = 0; q < 8; ++q)
@@ -467,13 +494,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
                 pb = col0 + 4;
               }
               const uint32_t aA = xa + (uint32_t)(pa * Cp2), aB = xa + (uint32_t)(pb * Cp2);
-              if (nval >= 8) {
-                if (ga.accumulate) batch(TT{}, TT{}, v, aA, aB, 8);
-                else batch(FF{}, TT{}, v, aA, aB, 8);
-              } else {
-                if (ga.accumulate) batch(TT{}, FF{}, v, aA, aB, nval);
-                else batch(FF{}, FF{}, v, aA, aB, nval);
-              }
+              if (nval >= 8) batch(TT{}, v, aA, aB, 8);
+              else batch(FF{}, v, aA, aB, nval);
             }
           } else {
             // upsampled source: columns 4w..4w+3 are the four children of half-resolution pixel low0 + w
@@ -485,18 +507,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
               const uint32_t a0 = xa + (uint32_t)((col0 >> 2) * Cp2);
               const bool ok1 = col0 + 4 < sp.nfull;
               const float x0 = lds_bf16(a0), x1 = ok1 ? lds_bf16(a0 + Cp2) : 0.f;
-              float g0 = 0.f, g1 = 0.f;
-              if (ga.accumulate) {
-                g0 = lds_bf16(a0 + gdelta);
-                g1 = ok1 ? lds_bf16(a0 + Cp2 + gdelta) : 0.f;
-              }
               const float d0 = fmaf(x0, sc, sh) > 0.f ? (v[0] + v[1]) + (v[2] + v[3]) : 0.f;
               const float d1 = (ok1 && fmaf(x1, sc, sh) > 0.f) ? (v[4] + v[5]) + (v[6] + v[7]) : 0.f;
               a_db += d0 + d1;
               a_dg = fmaf(d0, fmaf(x0, is, nmi), a_dg);
               a_dg = fmaf(d1, fmaf(x1, is, nmi), a_dg);
-              sts_u16(a0 + gdelta, __bfloat16_as_ushort(__float2bfloat16_rn(fmaf(gm, d0, g0))));
-              if (ok1) sts_u16(a0 + Cp2 + gdelta, __bfloat16_as_ushort(__float2bfloat16_rn(fmaf(gm, d1, g1))));
+              sts_u16(a0 + gdelta, __bfloat16_as_ushort(__float2bfloat16_rn(gm * d0)));
+              if (ok1) sts_u16(a0 + Cp2 + gdelta, __bfloat16_as_ushort(__float2bfloat16_rn(gm * d1)));
             }
           }
           atomicAdd(p.dbeta + kg, a_db);
@@ -518,7 +535,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
         }
         int npc = 0;
         for (int s = 0; s < p.in.nseg; ++s) npc += (seg_chunk(s) == c);
-        for (int q = 0; q < 2 * npc; ++q) useB ^= 1u << ((jn + q) & 3);
+        for (int q = 0; q < 2 * npc; ++q) useB ^= 1u << ((jn + q) & (D2_NJOB - 1));
       }
       base_i = next_base(base_i, (int)tl);
     }
