@@ -95,14 +95,14 @@ def _cpu_step_fn(cfg, batch):
 
 def cpu_reference(cfg, sample_batch, iters, warmup=1):
     """The reference's algorithm (oracle port of models/cu_net.py + cu-net.py:175-183 loss/backward/RMSprop) on
-    the host cores.  The thread count is the fastest of {all cores, 64, 32, 16} on a one-image CU-Net-2 probe
+    the host cores.  The thread count is the fastest of {16, 32, 64, all cores} (ascending, stops at the first slowdown) on a one-image CU-Net-2 probe
     step (oneDNN/ATen oversubscribe badly on 100+ core hosts for these small convolutions).
     Returns (images_per_sec, threads_used)."""
     import torch
     cores = os.cpu_count() or 1
     probe_cfg = dict(cfg, layer_num=2, loss_num=2)
     best, best_t = None, cores
-    for t in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+    for t in sorted({min(cores, 16), min(cores, 32), min(cores, 64), cores}):   # ascending; stop once it gets slower
         torch.set_num_threads(t)
         fn = _cpu_step_fn(probe_cfg, 1)
         fn()
@@ -111,6 +111,8 @@ def cpu_reference(cfg, sample_batch, iters, warmup=1):
         dt = time.perf_counter() - t0
         if best is None or dt < best:
             best, best_t = dt, t
+        else:
+            break
     torch.set_num_threads(best_t)
     step = _cpu_step_fn(cfg, sample_batch)
     times = []

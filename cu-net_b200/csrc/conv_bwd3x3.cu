@@ -1,0 +1,376 @@
+// Fused backward of the dense-layer 3x3 conv (models/cu_net.py:47-48 conv2, bf16): backward-data AND
+// backward-filter in ONE persistent kernel.  Same math as cunet_conv_dgrad + cunet_conv_wgrad (taps == 9):
+//
+//   dgrad : dA[p][ci]        = sum_{tap,co} dT[p - off(tap)][co] * W[co][ci][tap]
+//   wgrad : dW[co][ci][tap] += sum_p        a[p][ci]           * dT[p - off(tap)][co],    a = relu(bn(x))
+//
+// Both contractions consume the SAME operand: the im2col of the output gradient, I[p][(tap, co)] = dT[p - off(tap)][co]
+// (zero outside the image).  The round-1 kernels built it twice, each time with nine scattered global gathers per
+// pixel and no prefetch (ncu, batch 24: dgrad 139 us + wgrad 124 us at 64x64, 50 + 42 us even for 4x4 images).
+// Here, per stage of 64 consecutive pixels:
+//   * G/T of the output for the 64 pixels + a one-row halo (W + 1 pixels each side) and the raw input x are
+//     CONTIGUOUS blocks of NHWC tensors: three 1-D TMA bulk copies land them in shared memory;
+//   * 4 transformer warps evaluate dT = a*G + b*(T - mu) + d (batch-norm backward form) while gathering smem -> smem
+//     into the swizzled operand image I[64 px][320] (5 sub-tiles of 64 rows x 128 B) and a = relu(bn(x)) into
+//     A[64 px][128] (2 sub-tiles);
+//   * one thread issues  D1[128 ci][64 px]     = Wimg[128 ci][320] * I^T        (K-major x K-major, fresh per stage)
+//                        D2[128 ci][320 (tap,co)] += A^T[128 ci][64 px] * I     (MN-major x MN-major, TMEM-resident
+//                                                                                for the CTA's whole pixel range);
+//   * 8 epilogue warps (thread = input channel = TMEM lane) apply the ReLU mask, accumulate dbeta / dgamma in
+//     registers and overwrite x IN PLACE with gamma*dz; one thread bulk-stores (or L2-reduce-adds) the block to G_x;
+//   * at the end D2 is added to the fp32 weight gradient (red.global.add, reference layout [co][ci][tap]).
+// HBM traffic per stage = G, T (8 KB) + x (16 KB) + G_x (16 KB): everything is read once and written once.
+#include "loaders.cuh"
+#include "host_util.h"
+#include <stdlib.h>
+
+namespace cunet {
+
+constexpr int B3_THREADS = 512;  // warp 0 landing producer | 1 store issuer | 2 MMA | 3 idle | 4-7 transformers | 8-15 epilogue
+constexpr int B3_R = 64;                            // pixels per stage
+constexpr int B3_SUB = B3_R * 128;                  // one sub-tile: 64 rows x 128 B
+constexpr int B3_W_BYTES = 5 * 16384;               // dgrad weight image: 5 K blocks x [128 rows][128 B]
+constexpr int B3_W_OFF = 0;
+constexpr int B3_B_OFF = B3_W_OFF + B3_W_BYTES;     // im2col operand: 5 sub-tiles
+constexpr int B3_A_OFF = B3_B_OFF + 5 * B3_SUB;     // activation operand: 2 sub-tiles
+constexpr int B3_X_OFF = B3_A_OFF + 2 * B3_SUB;     // raw x / outgoing G, double buffered: 2 x 16 KB
+constexpr int B3_GT_BYTES = 12544;                  // >= (64 + 2*(64 + 1)) rows x 64 B
+constexpr int B3_G_OFF = B3_X_OFF + 2 * 16384;
+constexpr int B3_T_OFF = B3_G_OFF + B3_GT_BYTES;
+constexpr int B3_TAIL_OFF = B3_T_OFF + B3_GT_BYTES;
+constexpr uint32_t B3_D1_COL = 320;                 // TMEM: D2 in columns [0, 320), D1 buffers at 320 and 384
+
+struct B3Tail {
+  uint64_t w_full, gt_full, gt_free, ops_ready, ops_free, done;
+  uint64_t x_full[2], x_free[2], d1_full[2], d1_free[2], g_ready[2];
+  uint32_t tmem_base;
+  BnSmem bn;
+  GradSmem gc;
+};
+
+__device__ __forceinline__ void b3_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void b3_bulk_red_add_bf16(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void b3_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void b3_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ float b3_lds_bf16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return __uint_as_float((uint32_t)v << 16);
+}
+__device__ __forceinline__ void b3_sts_u16(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint4 b3_lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
+__global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid_constant__ cunet_conv_dgrad_params p,
+                                                                     float* __restrict__ dw, int per) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  B3Tail* tail = reinterpret_cast<B3Tail*>(smem + B3_TAIL_OFF);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, W = p.W;
+  const int M = p.N * H * W;
+  const int total = (M + B3_R - 1) / B3_R;
+  const int st0 = (int)blockIdx.x * per;
+  const int st1 = min(total, st0 + per);
+  const int ns = max(0, st1 - st0);
+  const int halo = W + 1;
+
+  if (tid == 0) {
+    mbar_init(&tail->w_full, 1);
+    mbar_init(&tail->gt_full, 1);
+    mbar_init(&tail->gt_free, 4);
+    mbar_init(&tail->ops_ready, 4);
+    mbar_init(&tail->ops_free, 1);
+    mbar_init(&tail->done, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->x_full[b], 1);
+      mbar_init(&tail->x_free[b], 1);
+      mbar_init(&tail->d1_full[b], 1);
+      mbar_init(&tail->d1_free[b], 8);
+      mbar_init(&tail->g_ready[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&tail->tmem_base, 512);
+  compute_bn_coefs(p.in, &tail->bn, 128, tid, B3_THREADS);
+  compute_grad_coefs(p.dy, &tail->gc, tid, B3_THREADS);
+  {
+    // the operand image is zeroed once: its padding columns (K index >= 288) are never written again
+    const uint32_t b0 = smem_u32(smem + B3_B_OFF);
+    for (int i = tid; i < 5 * B3_SUB / 16; i += B3_THREADS) sts128(b0 + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp == 0) {
+    // ============================================================== landing producer
+    if (lane == 0 && ns > 0) {
+      mbar_arrive_expect_tx(&tail->w_full, (uint32_t)B3_W_BYTES);
+      bulk_g2s(smem + B3_W_OFF, p.wpack_dgrad, (uint32_t)B3_W_BYTES, &tail->w_full);
+      const char* xsrc = reinterpret_cast<const char*>(p.in.seg[0].ptr);
+      const char* gsrc = reinterpret_cast<const char*>(p.dy.g);
+      const char* tsrc = reinterpret_cast<const char*>(p.dy.t);
+      for (int i = 0; i < ns; ++i) {
+        const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
+        const uint32_t b = (uint32_t)i & 1u;
+        mbar_wait(&tail->x_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&tail->x_full[b], (uint32_t)(nv * 256));
+        bulk_g2s(smem + B3_X_OFF + b * 16384, xsrc + (long)m0 * 256, (uint32_t)(nv * 256), &tail->x_full[b]);
+        const int lo = max(0, m0 - halo), hi = min(M, m0 + nv + halo);
+        const uint32_t gb = (uint32_t)((hi - lo) * 64);
+        mbar_wait(&tail->gt_free, ((uint32_t)i & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&tail->gt_full, 2u * gb);
+        bulk_g2s(smem + B3_G_OFF, gsrc + (long)lo * 64, gb, &tail->gt_full);
+        bulk_g2s(smem + B3_T_OFF, tsrc + (long)lo * 64, gb, &tail->gt_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================== G store issuer
+    if (lane == 0) {
+      char* G = reinterpret_cast<char*>(p.gacc[0].G);
+      for (int i = 0; i < ns; ++i) {
+        const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
+        const uint32_t b = (uint32_t)i & 1u;
+        mbar_wait(&tail->g_ready[b], ((uint32_t)i >> 1) & 1u);
+        const uint8_t* src = smem + B3_X_OFF + b * 16384;
+        if (p.gacc[0].accumulate) b3_bulk_red_add_bf16(G + (long)m0 * 256, src, (uint32_t)(nv * 256));
+        else b3_bulk_s2g(G + (long)m0 * 256, src, (uint32_t)(nv * 256));
+        b3_bulk_commit();
+        b3_bulk_wait_read0();
+        mbar_arrive(&tail->x_free[b]);
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================== MMA issuer
+    if (lane == 0 && ns > 0) {
+      const uint32_t idesc_d = make_idesc(Elem<bf16>::FMT, 128, 64, 0, 0);
+      const uint32_t idesc_w1 = make_idesc(Elem<bf16>::FMT, 128, 192, 1, 1);
+      const uint32_t idesc_w2 = make_idesc(Elem<bf16>::FMT, 128, 128, 1, 1);
+      const uint32_t wA = smem_u32(smem + B3_W_OFF), bB = smem_u32(smem + B3_B_OFF), aA = smem_u32(smem + B3_A_OFF);
+      mbar_wait(&tail->w_full, 0);
+      for (int i = 0; i < ns; ++i) {
+        const uint32_t b = (uint32_t)i & 1u;
+        mbar_wait(&tail->ops_ready, (uint32_t)i & 1u);
+        mbar_wait(&tail->d1_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d1 = tmem + B3_D1_COL + b * 64u;
+#pragma unroll
+        for (int kb = 0; kb < 5; ++kb) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kb == 4 && kk >= 2) break;  // K index >= 288: padding
+            umma<bf16>(d1, make_sdesc(wA + kb * 16384 + kk * 32, 16, 1024),
+                       make_sdesc(bB + kb * B3_SUB + kk * 32, 16, 1024), idesc_d, (uint32_t)((kb | kk) != 0));
+          }
+        }
+        tc_commit(&tail->d1_full[b]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t acc = (uint32_t)((i | kk) != 0);
+          const uint64_t ad = make_sdesc_mn<bf16>(aA + kk * 2048, B3_SUB);
+          umma<bf16>(tmem, ad, make_sdesc_mn<bf16>(bB + kk * 2048, B3_SUB), idesc_w1, acc);
+          umma<bf16>(tmem + 192, ad, make_sdesc_mn<bf16>(bB + 3 * B3_SUB + kk * 2048, B3_SUB), idesc_w2, acc);
+        }
+        tc_commit(&tail->ops_free);
+      }
+      tc_commit(&tail->done);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================================================== transformers (128 threads)
+    const int t = tid - 128;
+    const int c4 = t & 3, r0 = t >> 2;   // im2col: 16-byte column (8 output channels) x rows r0, r0 + 32
+    const int cc = t & 15, rb = t >> 4;  // activation: 16-byte column (8 input channels) x rows rb + 8q
+    GradCoef<bf16> gcf;
+    gcf.load(&tail->gc, c4 * 8);
+    ActCoef<bf16> acf;
+    acf.load(&tail->bn, cc * 8);
+    const uint32_t bbase = smem_u32(smem + B3_B_OFF), abase = smem_u32(smem + B3_A_OFF);
+    const uint32_t gl = smem_u32(smem + B3_G_OFF) + (uint32_t)c4 * 16u, tl = smem_u32(smem + B3_T_OFF) + (uint32_t)c4 * 16u;
+    for (int i = 0; i < ns; ++i) {
+      const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
+      const int lo = max(0, m0 - halo);
+      const uint32_t b = (uint32_t)i & 1u;
+      mbar_wait(&tail->gt_full, (uint32_t)i & 1u);
+      mbar_wait(&tail->x_full[b], ((uint32_t)i >> 1) & 1u);
+      mbar_wait(&tail->ops_free, ((uint32_t)i & 1u) ^ 1u);  // MMAs of the previous stage no longer read the operands
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = r0 + 32 * rr;
+        const int m = m0 + r;
+        int n = 0, h = 0, w = 0;
+        const bool rv = r < nv;
+        if (rv) pix_split(m, H, W, n, h, w);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          // out(q) reads in(q + off)  =>  in(p) receives from out(p - off)
+          const int hs = h - dy, ws = w - dx;
+          uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
+          if (rv && (unsigned)hs < (unsigned)H && (unsigned)ws < (unsigned)W) {
+            const uint32_t loc = (uint32_t)(m - dy * W - dx - lo) * 64u;
+            GradRaw<bf16> raw;
+            raw.g = b3_lds128(gl + loc);
+            raw.t = b3_lds128(tl + loc);
+            o = gcf.apply(p.dy, raw, lo_unused);
+          }
+          sts128(bbase + (uint32_t)(tap >> 1) * B3_SUB + tile_off(r, ((tap & 1) << 2) | c4), o);
+        }
+      }
+      {
+        const uint32_t xb = smem_u32(smem + B3_X_OFF + b * 16384) + (uint32_t)cc * 16u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = rb + 8 * q;
+          uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
+          if (r < nv) o = acf.apply(b3_lds128(xb + (uint32_t)r * 256u), lo_unused);
+          sts128(abase + (uint32_t)(cc >> 3) * B3_SUB + tile_off(r, cc & 7), o);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tail->ops_ready);
+        mbar_arrive(&tail->gt_free);
+      }
+    }
+  } else if (warp >= 8) {
+    // ============================================================== epilogue (256 threads)
+    const int e = warp - 8;
+    const int qd = warp & 3, hf = e >> 2;  // TMEM lane quarter (hardware: warp % 4), pixel-column half
+    const int k = qd * 32 + lane;          // input channel
+    const float sc = tail->bn.scale[k], sh = tail->bn.shift[k], is = tail->bn.istd[k];
+    const float nmi = -tail->bn.mean[k] * is;  // xhat = x * istd - mean * istd
+    const float gm = p.in.gamma[k];
+    float a_db = 0.f, a_dg = 0.f;
+    for (int i = 0; i < ns; ++i) {
+      const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
+      const uint32_t b = (uint32_t)i & 1u;
+      mbar_wait(&tail->d1_full[b], ((uint32_t)i >> 1) & 1u);
+      mbar_wait(&tail->x_full[b], ((uint32_t)i >> 1) & 1u);  // completed long ago: acquires the landed x for this thread
+      tc_fence_after();
+      const uint32_t xa = smem_u32(smem + B3_X_OFF + b * 16384) + (uint32_t)k * 2u;
+      const uint32_t tb = tmem + B3_D1_COL + b * 64u + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 1
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const int col0 = hf * 32 + g8 * 8;
+        const int nval = nv - col0;
+        if (nval <= 0) break;
+        float v[8];
+        tmem_ld8(tb + (uint32_t)col0, v);
+        const uint32_t a0 = xa + (uint32_t)col0 * 256u;
+        float x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = q < nval ? b3_lds_bf16(a0 + (uint32_t)q * 256u) : 0.f;
+        uint16_t gb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const bool on = fmaf(x[q], sc, sh) > 0.f && q < nval;
+          const float dz = on ? v[q] : 0.f;
+          a_db += dz;
+          a_dg = fmaf(dz, fmaf(x[q], is, nmi), a_dg);
+          gb[q] = __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < nval) b3_sts_u16(a0 + (uint32_t)q * 256u, gb[q]);
+      }
+      fence_proxy_async();  // G written over x -> visible to the bulk store
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tail->g_ready[b]);
+        mbar_arrive(&tail->d1_free[b]);
+      }
+    }
+    if (ns > 0) {
+      atomicAdd(p.dbeta + k, a_db);
+      atomicAdd(p.dgamma + k, a_dg);
+      if (p.gacc[0].gstats) {
+        // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma)  (see conv_dgrad_v2.cu)
+        atomicAdd(p.gacc[0].gstats + k, (double)(gm * a_db));
+        atomicAdd(p.gacc[0].gstats + 128 + k, (double)(gm * a_dg));
+      }
+      // ---- weight gradient: D2[128 ci][(tap, co)] -> dW[co][ci][tap]
+      mbar_wait(&tail->done, 0);
+      tc_fence_after();
+      for (int col = hf * 8; col < 288; col += 16) {
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)col, v);
+        const int tap = col >> 5, co0 = col & 31;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(dw + ((long)(co0 + q) * 128 + k) * 9 + tap, v[q]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace cunet
+using namespace cunet;
+
+// 1: handled by the fused kernel; 0: not eligible (caller runs the two generic kernels); <0: error
+static int conv_bwd3x3_try(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, cudaStream_t st) {
+  static const bool off = getenv("CUNET_BWD3X3_OFF") != nullptr;
+  if (off) return 0;
+  if (d->dtype != CUNET_BF16 || w->dtype != CUNET_BF16 || d->taps != 9 || w->taps != 9) return 0;
+  if (d->Cout != 32 || d->CoutPad != 32 || w->Cout != 32) return 0;
+  if (d->dy.C != 32 || d->dy.ld != 32 || d->dy.mode != 1 || d->dy.pooled) return 0;
+  if (d->in.nseg != 1 || d->in.bn_train != 1) return 0;
+  const cunet_seg& sg = d->in.seg[0];
+  if (sg.C != 128 || sg.ld != 128 || sg.up) return 0;
+  if (!d->gacc[0].G || d->gacc[0].ld != 128) return 0;
+  if (w->dw_cin != 0 && w->dw_cin != 128) return 0;
+  if (d->W > 64 || d->W < 1 || d->H < 1) return 0;
+  // same op on both sides
+  if (w->in.seg[0].ptr != sg.ptr || w->dy.g != d->dy.g || w->dy.t != d->dy.t || w->N != d->N || w->H != d->H ||
+      w->W != d->W)
+    return 0;
+  const long M = (long)d->N * d->H * d->W;
+  if (M <= 0) return 1;
+  if (M > (1L << 30)) return 0;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int total = (int)((M + B3_R - 1) / B3_R);
+  const int per = (total + sms - 1) / sms;
+  const int grid = (total + per - 1) / per;
+  const size_t smem = B3_TAIL_OFF + sizeof(B3Tail) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv_bwd3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_bwd3x3 attr", e);
+  conv_bwd3x3_kernel<<<grid, B3_THREADS, smem, st>>>(*d, w->dw, per);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_bwd3x3 launch", e);
+  return 1;
+}
+
+extern "C" int cunet_conv_bwd3x3(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, void* stream) {
+  if (!d || !w) return cunet_fail("conv_bwd3x3: null params");
+  const int r = conv_bwd3x3_try(d, w, reinterpret_cast<cudaStream_t>(stream));
+  if (r != 0) return r < 0 ? r : 0;
+  const int rc = cunet_conv_dgrad(d, stream);
+  if (rc != 0) return rc;
+  return cunet_conv_wgrad(w, stream);
+}

@@ -287,15 +287,20 @@ class Engine(object):
             dp.wpack_dgrad, dp.Cout, dp.CoutPad = self.wdg[op.conv], op.cout, op.cout_pad
             dp.dgamma, dp.dbeta = self._gp(op.norm + ".weight"), self._gp(op.norm + ".bias")
             dp.dtype = self.dtype
-            calls.append((lib.cunet_conv_dgrad, dp))
             self.call_index[(op.name, "dgrad")] = dp
             wp = L.ConvWgradParams()
             self._concat(wp.inp, op, 1)
             self._grad_src(wp.dy, op.out, op)
             wp.N, wp.H, wp.W, wp.taps, wp.Cout = N, op.res, op.res, op.taps, op.cout
             wp.dw, wp.nsplit, wp.dtype, wp.dw_cin = self._gp(op.conv + ".weight"), 0, self.dtype, 0
-            wcalls.append((len(calls) - 1, lib.cunet_conv_wgrad, wp))      # may start once dgrad #k may start
             self.call_index[(op.name, "wgrad")] = wp
+            if op.taps == 9 and self.dtype == L.BF16:
+                # dense-layer 3x3: backward-data and backward-filter share the im2col of the output gradient ->
+                # one fused launch on the main stream (csrc/conv_bwd3x3.cu)
+                calls.append((lib.cunet_conv_bwd3x3, (dp, wp)))
+            else:
+                calls.append((lib.cunet_conv_dgrad, dp))
+                wcalls.append((len(calls) - 1, lib.cunet_conv_wgrad, wp))  # may start once dgrad #k may start
         # stem backward: parameter-gradient reduction, dy, conv0 wgrad
         for phase in (0, 1):
             sb = L.StemBwdParams()
@@ -330,14 +335,20 @@ class Engine(object):
         st = L.stream_ptr()
         probes = getattr(self, "probes", None)
         for fn, prm in calls:
-            ev = probes.get(id(prm)) if probes else None
+            ev = probes.get(id(prm[0] if isinstance(prm, tuple) else prm)) if probes else None
             if ev is not None:
                 ev[0].record()
-            rc = fn(C.byref(prm), st)
+            rc = self._launch(fn, prm, st)
             if ev is not None:
                 ev[1].record()
             if rc != 0:
                 L.check(rc, fn.__name__)
+
+    @staticmethod
+    def _launch(fn, prm, st):
+        if isinstance(prm, tuple):
+            return fn(*[C.byref(q) for q in prm], st)
+        return fn(C.byref(prm), st)
 
     def pack_weights(self):
         L.pack_weights(self.pack_descs.data_ptr(), self.n_pack, self.dtype)
@@ -396,7 +407,7 @@ class Engine(object):
                 if rc != 0:
                     L.check(rc, wfn.__name__)
                 k += 1
-            rc = fn(C.byref(prm), st_main)
+            rc = self._launch(fn, prm, st_main)
             if rc != 0:
                 L.check(rc, fn.__name__)
         ev = self._evpool[-1]

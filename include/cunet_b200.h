@@ -143,6 +143,13 @@ typedef struct {
 
 int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream);
 
+/* Fused backward of the dense-layer 3x3 conv (models/cu_net.py:47-48, conv2 128 -> 32): exactly
+ * cunet_conv_dgrad(d) followed by cunet_conv_wgrad(w) for the SAME op (same `in`, same `dy`), in one launch.
+ * bf16, one 128-channel source, Cout == 32, batch-norm-form dy, W <= 64 run in the fused persistent kernel
+ * (the im2col of the output gradient is built once in shared memory and feeds both contractions); every
+ * other configuration falls back to the two calls above, in that order, on `stream`. */
+int cunet_conv_bwd3x3(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, void* stream);
+
 /* ---- stem: conv0 7x7 s2 p3 -> norm0 -> relu0 -> pool0 (models/cu_net.py:299-304) ------------------
  * conv0 runs on the tensor cores through cunet_conv_fwd / cunet_conv_wgrad with an identity input
  * (bn_train == 2) over an im2col matrix [N*Ho*Wo][160] (147 = 3*7*7 columns in the reference's

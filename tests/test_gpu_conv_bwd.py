@@ -158,3 +158,73 @@ def test_conv_dgrad(case, dtype_name):
         assert _relerr(gst[i][:c], st_ref[:c]) < tol and _relerr(gst[i][c:], st_ref[c:]) < tol, "gstats %d" % i
     assert _relerr(dbeta, db_ref) < tol, "dbeta %g" % _relerr(dbeta, db_ref)
     assert _relerr(dgamma, dg_ref) < tol, "dgamma %g" % _relerr(dgamma, dg_ref)
+
+
+FUSED_CASES = [
+    # name, n, h, w, accumulate
+    ("16x16", 2, 16, 16, 0),
+    ("4x4_tail", 3, 4, 4, 0),          # 48 pixels: one partial stage
+    ("4x4_b24", 24, 4, 4, 1),          # the network's neck: 6 stages, several images per stage
+    ("8x8", 3, 8, 8, 1),
+    ("32x32", 5, 32, 32, 0),           # 80 stages
+    ("64x64", 4, 64, 64, 1),           # 256 stages, > 148 CTAs' worth: multi-stage CTAs, halo = 65 rows
+    ("64x64_b24", 24, 64, 64, 0),      # the bench shape: 1536 stages, 11 per CTA
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_conv_bwd3x3_fused(case):
+    """cunet_conv_bwd3x3 (one fused launch) == dgrad + wgrad of the 3x3 dense-layer conv, bf16."""
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.BF16
+    name, n, h, w, accumulate = case
+    seg_c, ups, cout, taps, dy_mode = [128], [0], 32, 9, "bn"
+    cs = make_case(lib, dtype, n, h, w, seg_c, ups, cout, taps, dy_mode, None, seed=3)
+    dev, td = cs["dev"], cs["td"]
+    nbytes = lib.pack_dgrad_bytes(128, taps, 32, dtype)
+    wpack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    desc = lib.PackDesc(cs["weight"].data_ptr(), None, wpack.data_ptr(), cout, 128, taps, 32)
+    desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).to(dev)
+    lib.pack_weights(desc_dev.data_ptr(), 1, dtype)
+
+    dp = lib.ConvDgradParams()
+    fill_concat(dp.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"],
+                cs["gamma"], True)
+    fill_grad_src(dp.dy, cs, dy_mode)
+    x = cs["srcs"][0]
+    gen = torch.Generator(device="cpu").manual_seed(99)
+    g0 = (torch.randn(x.shape, generator=gen) * 0.05).to(dev).to(td) if accumulate else \
+        torch.full(x.shape, float("nan"), device=dev, dtype=td)
+    G0 = g0.clone()
+    gst = torch.zeros(256, dtype=torch.float64, device=dev)
+    dp.gacc[0].G, dp.gacc[0].gstats, dp.gacc[0].ld, dp.gacc[0].accumulate = g0.data_ptr(), gst.data_ptr(), 128, accumulate
+    dgamma = torch.zeros(128, device=dev)
+    dbeta = torch.zeros(128, device=dev)
+    dp.N, dp.H, dp.W, dp.taps = n, h, w, taps
+    dp.wpack_dgrad, dp.Cout, dp.CoutPad = wpack.data_ptr(), cout, 32
+    dp.dgamma, dp.dbeta, dp.dtype = dgamma.data_ptr(), dbeta.data_ptr(), dtype
+
+    dw = torch.zeros(cout, 128, taps, device=dev)
+    wp = lib.ConvWgradParams()
+    fill_concat(wp.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"],
+                cs["gamma"], True)
+    fill_grad_src(wp.dy, cs, dy_mode)
+    wp.N, wp.H, wp.W, wp.taps, wp.Cout = n, h, w, taps, cout
+    wp.dw, wp.nsplit, wp.dtype = dw.data_ptr(), 0, dtype
+
+    lib.conv_bwd3x3(dp, wp)
+    torch.cuda.synchronize()
+
+    outs, dg_ref, db_ref, dw_ref = reference(cs, n, h, w, ups, dy_mode)
+    tol = 2.5e-2
+    exp = outs[0] + (G0.float() if accumulate else 0)
+    assert torch.isfinite(g0.float()).all(), "unwritten rows in G"
+    err = _relerr(g0.float(), exp)
+    assert err < tol, "%s G rel err %g" % (name, err)
+    st_ref = ops_ref.gstats_of(outs[0], x, cs["stats"][0], cs["counts"][0])
+    assert _relerr(gst[:128], st_ref[:128]) < tol and _relerr(gst[128:], st_ref[128:]) < tol, "gstats"
+    assert _relerr(dbeta, db_ref) < tol, "dbeta %g" % _relerr(dbeta, db_ref)
+    assert _relerr(dgamma, dg_ref) < tol, "dgamma %g" % _relerr(dgamma, dg_ref)
+    errw = _relerr(dw.reshape(cout, 128, -1), dw_ref.reshape(cout, 128, -1))
+    assert errw < 2e-2, "%s dW rel err %g" % (name, errw)
