@@ -77,6 +77,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+// Programmatic dependent launch (launch attribute set by cunet_launch, host_util.h).  wait: block until every
+// prerequisite grid has completed and its memory is visible (no-op for a normal launch); launch: let the next
+// kernel in the stream start its prologue (barrier init, TMEM allocation) while this one is still running.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -105,14 +105,16 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tail->tmem_base, 512);
-  compute_bn_coefs(p.in, &tail->bn, 128, tid, B3_THREADS);
-  compute_grad_coefs(p.dy, &tail->gc, tid, B3_THREADS);
   {
     // the operand image is zeroed once: its padding columns (K index >= 288) are never written again
     const uint32_t b0 = smem_u32(smem + B3_B_OFF);
     for (int i = tid; i < 5 * B3_SUB / 16; i += B3_THREADS) sts128(b0 + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
     fence_proxy_async();
   }
+  griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
+  griddep_launch();
+  compute_bn_coefs(p.in, &tail->bn, 128, tid, B3_THREADS);
+  compute_grad_coefs(p.dy, &tail->gc, tid, B3_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -360,8 +362,7 @@ static int conv_bwd3x3_try(const cunet_conv_dgrad_params* d, const cunet_conv_wg
   const size_t smem = B3_TAIL_OFF + sizeof(B3Tail) + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_bwd3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_bwd3x3 attr", e);
-  conv_bwd3x3_kernel<<<grid, B3_THREADS, smem, st>>>(*d, w->dw, per);
-  e = cudaGetLastError();
+  e = cunet_launch(conv_bwd3x3_kernel, dim3(grid), dim3(B3_THREADS), smem, st, *d, w->dw, per);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_bwd3x3 launch", e);
   return 1;
 }

@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&tail->tmem_base, 256);
+  griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
+  griddep_launch();
   compute_bn_coefs(p.in, &tail->bn, nchunk_all * 128, tid, D2_THREADS);
   compute_grad_coefs(p.dy, &tail->gc, tid, D2_THREADS);
   tc_fence_before();
@@ -597,8 +599,7 @@ int cunet_conv_dgrad_v2_try(const cunet_conv_dgrad_params* p, cudaStream_t st) {
   const size_t smem = D2_TAIL_OFF + sizeof(D2Tail) + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_dgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_dgrad_v2 attr", e);
-  conv_dgrad_v2_kernel<<<grid, D2_THREADS, smem, st>>>(*p, ntiles, split);
-  e = cudaGetLastError();
+  e = cunet_launch(conv_dgrad_v2_kernel, dim3(grid), dim3(D2_THREADS), smem, st, *p, ntiles, split);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_dgrad_v2 launch", e);
   return 1;
 }

@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(FWD_THREADS, StageGeom<T>::MIN_CTAS) conv_fwd_
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(&tail->tmem_base, tmem_cols);
+  griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
+  griddep_launch();
   compute_bn_coefs(p.in, &tail->bn, nkb * E::KBE, tid, FWD_THREADS);
   PixGeom geom;
   geom.N = p.N; geom.H = p.H; geom.W = p.W; geom.M = p.N * p.H * p.W;
@@ -264,6 +266,8 @@ __global__ void __launch_bounds__(FWD_THREADS, StageGeom<T>::MIN_CTAS) conv_fwd_
 
 using namespace cunet;
 
+int cunet_conv_fwd3x3_try(const cunet_conv_fwd_params* p, cudaStream_t st);  // conv_fwd3x3.cu
+
 extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   if (!p) return cunet_fail("conv_fwd: null params");
   if (p->in.nseg < 1 || p->in.nseg > CUNET_MAX_SEG) return cunet_fail("conv_fwd: bad nseg");
@@ -283,6 +287,11 @@ extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   if (p->Cout % 4 && !p->out_fp32) return cunet_fail("conv_fwd: Cout must be a multiple of 4");
   const long M = (long)p->N * p->H * p->W;
   if (M <= 0) return 0;
+  if (p->taps == 9) {
+    // bf16 dense-layer 3x3 (128 -> 32, W in {8..64}): persistent shifted-descriptor kernel; everything else: this file
+    const int r = cunet_conv_fwd3x3_try(p, reinterpret_cast<cudaStream_t>(stream));
+    if (r != 0) return r < 0 ? r : 0;
+  }
   const long tiles = p->pool ? (M / 4 + 31) / 32 : (M + 127) / 128;
   const size_t smem = FWD_STAGES * (p->dtype == CUNET_BF16 ? StageGeom<bf16>::BYTES : StageGeom<float>::BYTES) +
                       sizeof(FwdSmemTail) + 1024;
@@ -291,11 +300,13 @@ extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   if (p->dtype == CUNET_BF16) {
     e = cudaFuncSetAttribute(conv_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd attr", e);
-    conv_fwd_kernel<bf16><<<(unsigned)tiles, FWD_THREADS, smem, st>>>(*p);
+    e = cunet_launch(conv_fwd_kernel<bf16>, dim3((unsigned)tiles), dim3(FWD_THREADS), smem, st, *p);
+    if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd launch", e);
   } else {
     e = cudaFuncSetAttribute(conv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd attr", e);
-    conv_fwd_kernel<float><<<(unsigned)tiles, FWD_THREADS, smem, st>>>(*p);
+    e = cunet_launch(conv_fwd_kernel<float>, dim3((unsigned)tiles), dim3(FWD_THREADS), smem, st, *p);
+    if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd launch", e);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return cunet_fail_cuda("conv_fwd launch", e);

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tail->tmem_base, 512);
+  griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
+  griddep_launch();
   compute_bn_coefs(p.in, &tail->bn, nchunk * 128, tid, W2_THREADS);
   compute_grad_coefs(p.dy, &tail->gc, tid, W2_THREADS);
   tc_fence_before();
@@ -341,8 +343,7 @@ int cunet_conv_wgrad_v2_try(const cunet_conv_wgrad_params* p, cudaStream_t st) {
   const size_t smem = W2_TAIL_OFF + sizeof(W2Tail) + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_wgrad_v2 attr", e);
-  conv_wgrad_v2_kernel<<<grid, W2_THREADS, smem, st>>>(*p, npad);
-  e = cudaGetLastError();
+  e = cunet_launch(conv_wgrad_v2_kernel, dim3(grid), dim3(W2_THREADS), smem, st, *p, npad);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_wgrad_v2 launch", e);
   return 1;
 }

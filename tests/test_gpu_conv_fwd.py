@@ -102,6 +102,13 @@ CASES = [
     ("1x1_tail", 3, 4, 4, [128, 32], [0, 0], 128, 1, False, True, False, None),
     ("1x1_pool_tail", 3, 4, 4, [128, 32, 32], [0, 0, 0], 128, 1, True, True, False, None),
     ("1x1_big", 4, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, False, True, False, None),
+    # dense-layer 3x3, persistent shifted-descriptor kernel in bf16 (conv_fwd3x3.cu): every resolution of the network
+    ("3x3_8x8", 3, 8, 8, [128], [0], 32, 9, False, True, False, None),
+    ("3x3_8x8_b24", 24, 8, 8, [128], [0], 32, 9, False, True, False, None),
+    ("3x3_32x32", 5, 32, 32, [128], [0], 32, 9, False, True, False, None),
+    ("3x3_64x64", 3, 64, 64, [128], [0], 32, 9, False, True, False, None),
+    ("3x3_64x64_b24", 24, 64, 64, [128], [0], 32, 9, False, True, False, None),
+    ("3x3_rect_eval", 2, 8, 16, [128], [0], 32, 9, False, False, False, None),
 ]
 
 
