@@ -10,7 +10,7 @@
 // Here, per stage of 64 consecutive pixels:
 //   * G/T of the output for the 64 pixels + a one-row halo (W + 1 pixels each side) and the raw input x are
 //     CONTIGUOUS blocks of NHWC tensors: three 1-D TMA bulk copies land them in shared memory;
-//   * 4 transformer warps evaluate dT = a*G + b*(T - mu) + d (batch-norm backward form) while gathering smem -> smem
+//   * 8 transformer warps evaluate dT = a*G + b*(T - mu) + d (batch-norm backward form) while gathering smem -> smem
 //     into the swizzled operand image I[64 px][320] (5 sub-tiles of 64 rows x 128 B) and a = relu(bn(x)) into
 //     A[64 px][128] (2 sub-tiles);
 //   * one thread issues  D1[128 ci][64 px]     = Wimg[128 ci][320] * I^T        (K-major x K-major, fresh per stage)
@@ -18,7 +18,8 @@
 //                                                                                for the CTA's whole pixel range);
 //   * 8 epilogue warps (thread = input channel = TMEM lane) apply the ReLU mask, accumulate dbeta / dgamma in
 //     registers and overwrite x IN PLACE with gamma*dz; one thread bulk-stores (or L2-reduce-adds) the block to G_x;
-//   * at the end D2 is added to the fp32 weight gradient (red.global.add, reference layout [co][ci][tap]).
+//   * at the end D2 is transposed through shared memory and added to the fp32 weight gradient with coalesced
+//     red.global.add (reference layout [co][ci][tap]).
 // HBM traffic per stage = G, T (8 KB) + x (16 KB) + G_x (16 KB): everything is read once and written once.
 #include "loaders.cuh"
 #include "host_util.h"
@@ -26,7 +27,7 @@
 
 namespace cunet {
 
-constexpr int B3_THREADS = 512;  // warp 0 landing producer | 1 store issuer | 2 MMA | 3 idle | 4-7 transformers | 8-15 epilogue
+constexpr int B3_THREADS = 640;  // warp 0 landing producer | 1 store issuer | 2 MMA | 3 idle | 4-11 transformers | 12-19 epilogue
 constexpr int B3_R = 64;                            // pixels per stage
 constexpr int B3_SUB = B3_R * 128;                  // one sub-tile: 64 rows x 128 B
 constexpr int B3_W_BYTES = 5 * 16384;               // dgrad weight image: 5 K blocks x [128 rows][128 B]
@@ -35,17 +36,18 @@ constexpr int B3_B_OFF = B3_W_OFF + B3_W_BYTES;     // im2col operand: 5 sub-til
 constexpr int B3_A_OFF = B3_B_OFF + 5 * B3_SUB;     // activation operand: 2 sub-tiles
 constexpr int B3_X_OFF = B3_A_OFF + 2 * B3_SUB;     // raw x / outgoing G, double buffered: 2 x 16 KB
 constexpr int B3_GT_BYTES = 12544;                  // >= (64 + 2*(64 + 1)) rows x 64 B
-constexpr int B3_G_OFF = B3_X_OFF + 2 * 16384;
-constexpr int B3_T_OFF = B3_G_OFF + B3_GT_BYTES;
-constexpr int B3_TAIL_OFF = B3_T_OFF + B3_GT_BYTES;
+constexpr int B3_G_OFF = B3_X_OFF + 2 * 16384;      // landed G / T with halo, double buffered: [buf][G | T]
+constexpr int B3_TAIL_OFF = B3_G_OFF + 4 * B3_GT_BYTES;
+constexpr int B3_COEF_OFF = B3_X_OFF;               // BnSmem + GradSmem live in the x buffers during the prologue only
+constexpr int B3_STG_LD = 169;                      // dW staging [128 ci][16 co][9 taps] (+9: odd stride, == 9 mod 32)
 constexpr uint32_t B3_D1_COL = 320;                 // TMEM: D2 in columns [0, 320), D1 buffers at 320 and 384
+static_assert(sizeof(BnSmem) <= 8192 && sizeof(GradSmem) <= 8192, "coefficient overlay");
+static_assert(128 * B3_STG_LD * 4 <= B3_A_OFF, "dW staging must fit the (dead) weight + operand regions");
 
 struct B3Tail {
-  uint64_t w_full, gt_full, gt_free, ops_ready, ops_free, done;
-  uint64_t x_full[2], x_free[2], d1_full[2], d1_free[2], g_ready[2];
+  uint64_t w_full, ops_ready, ops_free, done;
+  uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[2], d1_free[2], g_ready[2];
   uint32_t tmem_base;
-  BnSmem bn;
-  GradSmem gc;
 };
 
 __device__ __forceinline__ void b3_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
@@ -74,6 +76,8 @@ __device__ __forceinline__ uint4 b3_lds128(uint32_t saddr) {
   return v;
 }
 
+__device__ __forceinline__ void b3_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid_constant__ cunet_conv_dgrad_params p,
                                                                      float* __restrict__ dw, int per) {
   extern __shared__ uint8_t smem_raw[];
@@ -90,12 +94,12 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
 
   if (tid == 0) {
     mbar_init(&tail->w_full, 1);
-    mbar_init(&tail->gt_full, 1);
-    mbar_init(&tail->gt_free, 4);
-    mbar_init(&tail->ops_ready, 4);
+    mbar_init(&tail->ops_ready, 8);
     mbar_init(&tail->ops_free, 1);
     mbar_init(&tail->done, 1);
     for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->gt_full[b], 1);
+      mbar_init(&tail->gt_free[b], 8);
       mbar_init(&tail->x_full[b], 1);
       mbar_init(&tail->x_free[b], 1);
       mbar_init(&tail->d1_full[b], 1);
@@ -113,12 +117,37 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
   }
   griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
   griddep_launch();
-  compute_bn_coefs(p.in, &tail->bn, 128, tid, B3_THREADS);
-  compute_grad_coefs(p.dy, &tail->gc, tid, B3_THREADS);
+  BnSmem* bn = reinterpret_cast<BnSmem*>(smem + B3_COEF_OFF);
+  GradSmem* gc = reinterpret_cast<GradSmem*>(smem + B3_COEF_OFF + 8192);
+  compute_bn_coefs(p.in, bn, 128, tid, B3_THREADS);
+  compute_grad_coefs(p.dy, gc, tid, B3_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
+
+  // per-role coefficients go to registers; after the next barrier the coefficient area is the x landing buffer
+  const bool is_tr = warp >= 4 && warp < 12, is_ep = warp >= 12;
+  const int t = tid - 128;                 // transformer thread index (0..255)
+  const int c4 = t & 3, rI = t >> 2;       // im2col: 16-byte column (8 output channels) x pixel row rI
+  const int cc = t & 15, rb = t >> 4;      // activation: 16-byte column (8 input channels) x rows rb + 16q
+  const int e = warp - 12;
+  const int qd = warp & 3, hf = (e >> 2) & 1;  // epilogue: TMEM lane quarter (hardware: warp % 4), pixel-column half
+  const int k = qd * 32 + lane;                // epilogue: input channel
+  GradCoef<bf16> gcf;
+  ActCoef<bf16> acf;
+  float sc = 0.f, sh = 0.f, is = 0.f, nmi = 0.f;
+  if (is_tr) {
+    gcf.load(gc, c4 * 8);
+    acf.load(bn, cc * 8);
+  }
+  if (is_ep) {
+    sc = bn->scale[k];
+    sh = bn->shift[k];
+    is = bn->istd[k];
+    nmi = -bn->mean[k] * is;  // xhat = x * istd - mean * istd
+  }
+  __syncthreads();
 
   if (warp == 0) {
     // ============================================================== landing producer
@@ -130,16 +159,16 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       const char* tsrc = reinterpret_cast<const char*>(p.dy.t);
       for (int i = 0; i < ns; ++i) {
         const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
-        const uint32_t b = (uint32_t)i & 1u;
-        mbar_wait(&tail->x_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&tail->x_full[b], (uint32_t)(nv * 256));
-        bulk_g2s(smem + B3_X_OFF + b * 16384, xsrc + (long)m0 * 256, (uint32_t)(nv * 256), &tail->x_full[b]);
+        const uint32_t b = (uint32_t)i & 1u, fpar = (((uint32_t)i >> 1) & 1u) ^ 1u;
         const int lo = max(0, m0 - halo), hi = min(M, m0 + nv + halo);
         const uint32_t gb = (uint32_t)((hi - lo) * 64);
-        mbar_wait(&tail->gt_free, ((uint32_t)i & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&tail->gt_full, 2u * gb);
-        bulk_g2s(smem + B3_G_OFF, gsrc + (long)lo * 64, gb, &tail->gt_full);
-        bulk_g2s(smem + B3_T_OFF, tsrc + (long)lo * 64, gb, &tail->gt_full);
+        mbar_wait(&tail->gt_free[b], fpar);
+        mbar_arrive_expect_tx(&tail->gt_full[b], 2u * gb);
+        bulk_g2s(smem + B3_G_OFF + b * 2 * B3_GT_BYTES, gsrc + (long)lo * 64, gb, &tail->gt_full[b]);
+        bulk_g2s(smem + B3_G_OFF + b * 2 * B3_GT_BYTES + B3_GT_BYTES, tsrc + (long)lo * 64, gb, &tail->gt_full[b]);
+        mbar_wait(&tail->x_free[b], fpar);
+        mbar_arrive_expect_tx(&tail->x_full[b], (uint32_t)(nv * 256));
+        bulk_g2s(smem + B3_X_OFF + b * 16384, xsrc + (long)m0 * 256, (uint32_t)(nv * 256), &tail->x_full[b]);
       }
     }
   } else if (warp == 1) {
@@ -193,27 +222,19 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       }
       tc_commit(&tail->done);
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ============================================================== transformers (128 threads)
-    const int t = tid - 128;
-    const int c4 = t & 3, r0 = t >> 2;   // im2col: 16-byte column (8 output channels) x rows r0, r0 + 32
-    const int cc = t & 15, rb = t >> 4;  // activation: 16-byte column (8 input channels) x rows rb + 8q
-    GradCoef<bf16> gcf;
-    gcf.load(&tail->gc, c4 * 8);
-    ActCoef<bf16> acf;
-    acf.load(&tail->bn, cc * 8);
+  } else if (is_tr) {
+    // ============================================================== transformers (256 threads)
     const uint32_t bbase = smem_u32(smem + B3_B_OFF), abase = smem_u32(smem + B3_A_OFF);
-    const uint32_t gl = smem_u32(smem + B3_G_OFF) + (uint32_t)c4 * 16u, tl = smem_u32(smem + B3_T_OFF) + (uint32_t)c4 * 16u;
     for (int i = 0; i < ns; ++i) {
       const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
       const int lo = max(0, m0 - halo);
-      const uint32_t b = (uint32_t)i & 1u;
-      mbar_wait(&tail->gt_full, (uint32_t)i & 1u);
-      mbar_wait(&tail->x_full[b], ((uint32_t)i >> 1) & 1u);
+      const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
+      const uint32_t gl = smem_u32(smem + B3_G_OFF + b * 2 * B3_GT_BYTES) + (uint32_t)c4 * 16u, tl = gl + B3_GT_BYTES;
+      mbar_wait(&tail->gt_full[b], upar);
+      mbar_wait(&tail->x_full[b], upar);
       mbar_wait(&tail->ops_free, ((uint32_t)i & 1u) ^ 1u);  // MMAs of the previous stage no longer read the operands
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = r0 + 32 * rr;
+      {
+        const int r = rI;
         const int m = m0 + r;
         int n = 0, h = 0, w = 0;
         const bool rv = r < nv;
@@ -237,8 +258,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       {
         const uint32_t xb = smem_u32(smem + B3_X_OFF + b * 16384) + (uint32_t)cc * 16u;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = rb + 8 * q;
+        for (int q = 0; q < 4; ++q) {
+          const int r = rb + 16 * q;
           uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
           if (r < nv) o = acf.apply(b3_lds128(xb + (uint32_t)r * 256u), lo_unused);
           sts128(abase + (uint32_t)(cc >> 3) * B3_SUB + tile_off(r, cc & 7), o);
@@ -248,16 +269,11 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&tail->ops_ready);
-        mbar_arrive(&tail->gt_free);
+        mbar_arrive(&tail->gt_free[b]);
       }
     }
-  } else if (warp >= 8) {
+  } else if (is_ep) {
     // ============================================================== epilogue (256 threads)
-    const int e = warp - 8;
-    const int qd = warp & 3, hf = e >> 2;  // TMEM lane quarter (hardware: warp % 4), pixel-column half
-    const int k = qd * 32 + lane;          // input channel
-    const float sc = tail->bn.scale[k], sh = tail->bn.shift[k], is = tail->bn.istd[k];
-    const float nmi = -tail->bn.mean[k] * is;  // xhat = x * istd - mean * istd
     const float gm = p.in.gamma[k];
     float a_db = 0.f, a_dg = 0.f;
     for (int i = 0; i < ns; ++i) {
@@ -308,16 +324,35 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
         atomicAdd(p.gacc[0].gstats + k, (double)(gm * a_db));
         atomicAdd(p.gacc[0].gstats + 128 + k, (double)(gm * a_dg));
       }
-      // ---- weight gradient: D2[128 ci][(tap, co)] -> dW[co][ci][tap]
+    }
+    // ---- weight gradient: D2[128 ci][(tap, co)] -> dW[co][ci][tap].  A thread owns one ci (TMEM lane), but the
+    // reference layout has ci * 9 + tap contiguous per co: adding straight from registers put 32 different sectors
+    // under every warp-wide red (ncu: ~30 us of the kernel, even for a 6-CTA launch).  Instead the accumulator is
+    // transposed through the (now dead) weight / operand regions, 16 output channels at a time, and every warp
+    // adds 32 consecutive floats.  All CTAs run this (uniform barriers); ns == 0 CTAs do not exist (host: grid).
+    const int et = tid - 384;
+    float* stg = reinterpret_cast<float*>(smem);
+    if (ns > 0) {
       mbar_wait(&tail->done, 0);
       tc_fence_after();
-      for (int col = hf * 8; col < 288; col += 16) {
+    }
+#pragma unroll 1
+    for (int hh = 0; hh < 2 && ns > 0; ++hh) {
+      for (int j = hf; j < 18; j += 2) {
+        const int tap = j >> 1, c8 = (j & 1) * 8;
         float v[8];
-        tmem_ld8(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)col, v);
-        const int tap = col >> 5, co0 = col & 31;
+        tmem_ld8(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(tap * 32 + hh * 16 + c8), v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) atomicAdd(dw + ((long)(co0 + q) * 128 + k) * 9 + tap, v[q]);
+        for (int q = 0; q < 8; ++q) stg[k * B3_STG_LD + (c8 + q) * 9 + tap] = v[q];
       }
+      b3_named_bar(3, 256);
+      float* dst = dw + (long)hh * 16 * 1152;
+      for (int idx = et; idx < 16 * 1152; idx += 256) {
+        const int c16 = idx / 1152, r = idx - c16 * 1152;
+        const int ci = r / 9, tap = r - ci * 9;
+        atomicAdd(dst + idx, stg[ci * B3_STG_LD + c16 * 9 + tap]);
+      }
+      b3_named_bar(3, 256);
     }
   }
 
@@ -360,6 +395,7 @@ static int conv_bwd3x3_try(const cunet_conv_dgrad_params* d, const cunet_conv_wg
   const int per = (total + sms - 1) / sms;
   const int grid = (total + per - 1) / per;
   const size_t smem = B3_TAIL_OFF + sizeof(B3Tail) + 1024;
+  static_assert(B3_TAIL_OFF + sizeof(B3Tail) + 1024 <= 232448, "conv_bwd3x3 shared memory");
   cudaError_t e = cudaFuncSetAttribute(conv_bwd3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cunet_fail_cuda("conv_bwd3x3 attr", e);
   e = cunet_launch(conv_bwd3x3_kernel, dim3(grid), dim3(B3_THREADS), smem, st, *d, w->dw, per);

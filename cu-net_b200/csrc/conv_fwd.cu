@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(FWD_THREADS, StageGeom<T>::MIN_CTAS) conv_fwd_
 using namespace cunet;
 
 int cunet_conv_fwd3x3_try(const cunet_conv_fwd_params* p, cudaStream_t st);  // conv_fwd3x3.cu
+int cunet_conv_fwd_v2_try(const cunet_conv_fwd_params* p, cudaStream_t st);   // conv_fwd_v2.cu
 
 extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   if (!p) return cunet_fail("conv_fwd: null params");
@@ -287,6 +288,11 @@ extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   if (p->Cout % 4 && !p->out_fp32) return cunet_fail("conv_fwd: Cout must be a multiple of 4");
   const long M = (long)p->N * p->H * p->W;
   if (M <= 0) return 0;
+  if (p->taps == 1) {
+    // bf16 1x1 without pooling: persistent bulk-landing kernel
+    const int r = cunet_conv_fwd_v2_try(p, reinterpret_cast<cudaStream_t>(stream));
+    if (r != 0) return r < 0 ? r : 0;
+  }
   if (p->taps == 9) {
     // bf16 dense-layer 3x3 (128 -> 32, W in {8..64}): persistent shifted-descriptor kernel; everything else: this file
     const int r = cunet_conv_fwd3x3_try(p, reinterpret_cast<cudaStream_t>(stream));

@@ -109,6 +109,13 @@ CASES = [
     ("3x3_64x64", 3, 64, 64, [128], [0], 32, 9, False, True, False, None),
     ("3x3_64x64_b24", 24, 64, 64, [128], [0], 32, 9, False, True, False, None),
     ("3x3_rect_eval", 2, 8, 16, [128], [0], 32, 9, False, False, False, None),
+    # 1x1, persistent bulk-landing kernel in bf16 (conv_fwd_v2.cu): multi-tile CTAs, upsampled sources, partial tiles
+    ("1x1_320_up_b24", 24, 64, 64, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, False, True, False, None),
+    ("1x1_288_up_32", 6, 32, 32, [128, 128, 32], [1, 0, 0], 128, 1, False, True, False, None),
+    ("1x1_up_tail", 3, 4, 4, [128, 128, 32], [1, 0, 0], 128, 1, False, True, False, None),
+    ("1x1_256_b24", 24, 64, 64, [128, 128], [0, 0], 128, 1, False, True, False, None),
+    ("1x1_160_eval", 5, 16, 16, [128, 32], [0, 0], 128, 1, False, False, False, None),
+    ("head68_b24", 24, 64, 64, [128], [0], 68, 1, False, True, True, 80),
 ]
 
 
