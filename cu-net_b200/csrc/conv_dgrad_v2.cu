@@ -157,16 +157,16 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
   const uint32_t tmem = tail->tmem_base;
 
   // ---- job enumeration shared by all roles (per tile): G_out, [T_out], [idx], then per chunk and per segment
-  //      piece of the chunk: x, G_src.  Job j lives in slot j % 4.
+  //      piece of the chunk: x (whose landing area later holds the outgoing G increment).
   auto seg_chunk = [&](int s) { return tail->bn.seg_start[s] >> 7; };
   // Job order (identical in every role).  The dT jobs (G_out, T_out, idx) of the NEXT tile are issued before the
   // last chunk of the current tile when there are >= 2 chunks: the last chunk of this network's concats is the
-  // one with two pieces (four slots), and landing / transforming the next tile's dT behind it left a ~4 us
+  // one with two pieces, and landing / transforming the next tile's dT behind it left a ~4 us
   // bubble per tile in the in-kernel timeline (tools/trace_dgrad.py).
   int njc[4] = {0, 0, 0, 0}, prefix[4] = {0, 0, 0, 0};
   for (int s = 0; s < p.in.nseg; ++s) {
     const int cl = seg_chunk(s) - c0;  // local chunk index
-    if (cl >= 0 && cl < nchunk) njc[cl & 3] += 2;
+    if (cl >= 0 && cl < nchunk) njc[cl & 3] += 1;
   }
   for (int c = 1; c < 4; ++c) prefix[c] = prefix[c - 1] + njc[c - 1];
   const int NJ = prefix[nchunk - 1] + njc[nchunk - 1];
@@ -185,8 +185,11 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
     if (lane == 0) {
       uint32_t jn = 0, jh = 0;  // next job, oldest job not yet known to be released
       int pos = 0;              // absolute unit cursor of the landing ring
-      // size_bytes: extent of the job's area (a G area is also the staging buffer of the outgoing G even when
-      // nothing is loaded into it); load_bytes: what the bulk copy brings in (0 = just publish the area)
+      // size_bytes: extent of the job's area (an x area is also the staging buffer of the outgoing G: the epilogue
+      // overwrites x with gamma*dz in place, which halves a tile's landing footprint -- 15 of the 16 units for a
+      // 320-channel concat, so the next tile's dT jobs fit beside it; with separate x and G areas a tile needed 22
+      // units and the in-kernel timeline showed the next tile's G_out / T_out landing 7 us late);
+      // load_bytes: what the bulk copy brings in (0 = just publish the area)
       auto land = [&](const void* src, uint32_t load_bytes, uint32_t size_bytes, bool party_b) {
         int u = (int)((size_bytes + D2_UNIT - 1) / D2_UNIT);
         u = u < 1 ? 1 : u;
@@ -232,7 +235,6 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
             const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
             const uint32_t bytes = (uint32_t)(nx * sg.C * 2);
             land(reinterpret_cast<const char*>(sg.ptr) + (long)x0 * sg.C * 2, p.gacc[s].G ? bytes : 0u, bytes, true);
-            land(nullptr, 0u, bytes, true);  // staging area of the outgoing G increment (nothing to load)
           }
         }
         if (!early && i + 1 < ntile_cta) land_dt(tile + tstride);
@@ -380,8 +382,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
           for (int s = 0; s < p.in.nseg; ++s) {
             if (seg_chunk(s) != c) continue;
             const cunet_seg& sg = p.in.seg[s];
-            const uint32_t jgs = jn + 2 * j + 1;
-            mbar_arrive(&tail->job_empty[(jn + 2 * j) & (D2_NJOB - 1)]);  // the x area is free right away
+            const uint32_t jgs = jn + j;  // the piece's landing area: x on arrival, the outgoing G increment now
             if (p.gacc[s].G != nullptr) {
               const int x0 = sg.up ? sp.low0 : sp.full0, nx = sg.up ? sp.nlow : sp.nfull;
               char* dst = reinterpret_cast<char*>(p.gacc[s].G) + (long)x0 * sg.C * 2;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
           bulk_commit();
           bulk_wait_read0();  // the staging areas may be overwritten once the stores have read them
           if (it < 24) D2_TRACE(64 + it * 8 + 5);
-          for (int q = 0; q < j; ++q) mbar_arrive(&tail->job_empty[(jn + 2 * q + 1) & (D2_NJOB - 1)]);
+          for (int q = 0; q < j; ++q) mbar_arrive(&tail->job_empty[(jn + q) & (D2_NJOB - 1)]);
         }
         base_i = next_base(base_i, (int)tl);
       }
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
             ++j;
           }
         }
-        const uint32_t jx = jn + 2 * pj, jg = jx + 1;
+        const uint32_t jx = jn + pj;
         if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 0);
         mbar_wait(&tail->acc_full[buf], (it >> 1) & 1);
         tc_fence_after();
@@ -435,17 +436,16 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
           const cunet_seg& sg = p.in.seg[ps];
           const cunet_gacc& ga = p.gacc[ps];
           // parity = number of party-B jobs that used the slot before this one (pieces before pj in this chunk
-          // occupy other slots: a chunk has at most two pieces = four distinct slots)
-          const uint32_t ix = jx & (D2_NJOB - 1), ig = jg & (D2_NJOB - 1);
+          // occupy other slots)
+          const uint32_t ix = jx & (D2_NJOB - 1);
           mbar_wait(&tail->job_fullB[ix], (useB >> ix) & 1);
-          mbar_wait(&tail->job_fullB[ig], (useB >> ig) & 1);
           if (et == 0 && it < 24) D2_TRACE(64 + it * 8 + 2);
           const int kl = kg - tail->bn.seg_start[ps];
           const int Cp = sg.C, Cp2 = Cp * 2;
-          // shared-window addresses of this thread's channel in the x slot; the G slot sits gdelta bytes away
-          const int ux = tail->job_unit[ix], ug = tail->job_unit[ig];
+          // shared-window address of this thread's channel in the piece's landing area
+          const int ux = tail->job_unit[ix];
           const uint32_t xa = smem_u32(smem + ux * D2_UNIT) + (uint32_t)(kl * 2);
-          const uint32_t gdelta = (uint32_t)((ug - ux) * D2_UNIT);
+          constexpr uint32_t gdelta = 0;  // gamma*dz overwrites x in place (each element is read, then written, by one thread)
           const float sc = tail->bn.scale[kg], sh = tail->bn.shift[kg], is = tail->bn.istd[kg];
           const float nmi = -tail->bn.mean[kg] * is;  // xhat = x * istd - mean * istd
           const float gm = p.in.gamma[kg];
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) conv_dgrad_v2_kernel(const __gr
         }
         int npc = 0;
         for (int s = 0; s < p.in.nseg; ++s) npc += (seg_chunk(s) == c);
-        for (int q = 0; q < 2 * npc; ++q) useB ^= 1u << ((jn + q) & (D2_NJOB - 1));
+        for (int q = 0; q < npc; ++q) useB ^= 1u << ((jn + q) & (D2_NJOB - 1));
       }
       base_i = next_base(base_i, (int)tl);
     }
@@ -577,7 +577,7 @@ int cunet_conv_dgrad_v2_try(const cunet_conv_dgrad_params* p, cudaStream_t st) {
     up |= sg.up;
   }
   for (int c = 0; c < 8; ++c) pieces_max = per_chunk[c] > pieces_max ? per_chunk[c] : pieces_max;
-  if (pieces_max > 2) return 0;  // 4 landing slots: x and G of at most two pieces per chunk are resident together
+  if (pieces_max > 2) return 0;  // job-parity bookkeeping assumes at most two pieces per chunk
   if (cin > MAX_CIN) return 0;
   if (up || p->dy.pooled) {
     const int W = p->W, H = p->H;

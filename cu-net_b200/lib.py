@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcunet_b200.so")
+# CUNET_LIB: an alternate build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("CUNET_LIB") or os.path.join(_HERE, "libcunet_b200.so")
 _lib = None
 
 F32, BF16 = 0, 1
@@ -119,7 +120,7 @@ def load():
 # every symbol include/cunet_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "cunet_last_error", "cunet_abi_version",
-    "cunet_conv_fwd", "cunet_conv_dgrad", "cunet_debug_dgrad_trace", "cunet_conv_wgrad", "cunet_conv_bwd3x3", "cunet_pack_weights", "cunet_pack_fwd_bytes",
+    "cunet_conv_fwd", "cunet_debug_fwd_v2_min_tiles", "cunet_conv_dgrad", "cunet_debug_dgrad_trace", "cunet_conv_wgrad", "cunet_conv_bwd3x3", "cunet_pack_weights", "cunet_pack_fwd_bytes",
     "cunet_pack_dgrad_bytes", "cunet_stem_im2col", "cunet_stem_pool_fwd", "cunet_stem_bwd", "cunet_mse_decode",
     "cunet_decode_finalize", "cunet_bn_running_update", "cunet_rmsprop_step",
     "cunet_quant_forward", "cunet_quant_restore", "cunet_quant_grad", "cunet_quant_input_fwd",
@@ -146,6 +147,11 @@ def dptr(t):
 
 def conv_fwd(params):
     check(load().cunet_conv_fwd(C.byref(params), stream_ptr()), "cunet_conv_fwd")
+
+
+def debug_fwd_v2_min_tiles(min_tiles):
+    """Experiment switch of the 1x1 forward dispatch (see include/cunet_b200.h); returns the previous setting."""
+    return int(load().cunet_debug_fwd_v2_min_tiles(C.c_int(min_tiles)))
 
 
 def conv_dgrad(params):

@@ -143,6 +143,11 @@ typedef struct {
 
 int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream);
 
+/* debug / experiment switch: route bf16 1x1 forward calls with >= min_tiles 128-pixel tiles (and no pooling) to the
+ * persistent bulk-landing kernel (csrc/conv_fwd_v2.cu); < 0 (the default) keeps the round-1 kernel.  Returns the
+ * previous setting.  Also settable through the environment (CUNET_FWD_V2_MIN_TILES). */
+int cunet_debug_fwd_v2_min_tiles(int min_tiles);
+
 /* Fused backward of the dense-layer 3x3 conv (models/cu_net.py:47-48, conv2 128 -> 32): exactly
  * cunet_conv_dgrad(d) followed by cunet_conv_wgrad(w) for the SAME op (same `in`, same `dy`), in one launch.
  * bf16, one 128-channel source, Cout == 32, batch-norm-form dy, W <= 64 run in the fused persistent kernel

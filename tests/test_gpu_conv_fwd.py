@@ -142,3 +142,29 @@ def test_conv_fwd(case, dtype_name):
         # argmax positions must agree wherever the maximum is not a (near) tie
         agree = (pidx == ridx).float().mean().item()
         assert agree > (0.999 if dtype == lib.F32 else 0.97), agree
+
+
+V2_CASES = [c for c in CASES if c[7] == 1 and not c[8]]     # every 1x1 case without pooling
+
+
+@pytest.mark.parametrize("case", V2_CASES, ids=[c[0] for c in V2_CASES])
+def test_conv_fwd_v2(case):
+    """The opt-in persistent 1x1 forward kernel (conv_fwd_v2.cu) against the same references, bf16."""
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.BF16
+    name, n, h, w, seg_c, ups, cout, taps, pool, train, out_fp32, cout_pad = case
+    old = lib.debug_fwd_v2_min_tiles(1)
+    try:
+        out, ref, out_stats, _, _ = run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool, train, out_fp32,
+                                                 cout_pad)
+    finally:
+        lib.debug_fwd_v2_min_tiles(old)
+    got = out.float()[:, :cout]
+    assert torch.isfinite(got).all(), "kernel left unwritten / non-finite outputs"
+    err = _relerr(got, ref)
+    assert err < 1.5e-2, "%s rel err %g" % (name, err)
+    if out_fp32 and cout_pad and cout_pad > cout:
+        assert (out[:, cout:] == 0).all()
+    if out_stats is not None:
+        assert _relerr(out_stats, ops_ref.tensor_stats(got)) < 1e-4
