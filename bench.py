@@ -294,6 +294,14 @@ def main():
                         achieved=by / (t_ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
                         frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm"], tflops=flops / (t_ms * 1e-3) / 1e12)
     dom = roofs["dgrad"]
+    # DRAM traffic of the dominant kernel on this op: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+    # `ncu --set full` capture (profiles/traffic.json names the capture); not measurable from inside this process
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and cfg["dtype"] == "bf16":
+        tj = json.load(open(tpath)).get("conv_dgrad")
+        if tj:
+            traffic, traffic_src = tj["bytes"], tj["source"]
     train_gflop_img = (3.0 * plan.conv_flops_per_image() - 2.0 * 147 * 128 * 128 * 128) / 1e9
     tflops = value * train_gflop_img / 1e3
     line = dict(
@@ -303,12 +311,14 @@ def main():
         config=dict(workload=workload, global_batch=world * B, parallelism="dp%d" % world,
                     l2="working set (~%.1f GB of activations per step) far exceeds the 126 MB L2; no flush needed"
                        % (sum(a.numel() * a.element_size() for a in eng.act.values()) / 1e9),
-                    launch="cuda-graph replay" if not args.no_graph else "eager"),
+                    launch="cuda-graph replay" if not args.no_graph else "eager",
+                    pdl="programmatic dependent launch between the conv kernels: %s"
+                        % ("off" if os.environ.get("CUNET_PDL", "1") == "0" else "on")),
         e2e=dict(value=e2e, unit="images/s", ms_per_step=ms_e2e,
                  h2d_bytes_per_step=int(img_h.numel() * 4 + hm_h.numel() * 4), d2h_bytes_per_step=8),
         gpu_launches=int(eng.launches_per_train_step() * args.steps),
         roofline=dict(bound="hbm", achieved=dom["achieved"], peak=dom["peak"], unit="GB/s", frac=dom["frac"],
-                      traffic=None, kernel=dom["kernel"], op=dom["op"], us_per_launch=dom["us"],
+                      traffic=traffic, traffic_source=traffic_src, kernel=dom["kernel"], op=dom["op"], us_per_launch=dom["us"],
                       algorithmic_bytes=dom["bytes"], peak_source=pk["source"],
                       note="probe launches timed eagerly with CUDA events right after the timed region"),
         roofline_all=roofs,

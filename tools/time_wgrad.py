@@ -8,7 +8,7 @@ dtype = lib.BF16
 n,h,w,seg_c,ups,cout,taps,mode = 24,64,64,[128,128,32,32],[1,0,0,0],128,1,"bn"
 cs = make_case(lib, dtype, n,h,w,seg_c,ups,cout,taps,mode,None)
 dw = torch.zeros(cout, cs["cin"], taps, device="cuda")
-for nsplit in [0, 49, 74, 98, 99, 148, 196, 296]:
+for nsplit in [0, 148]:
     p = lib.ConvWgradParams()
     fill_concat(p.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"], cs["gamma"], True)
     fill_grad_src(p.dy, cs, mode)
