@@ -197,7 +197,7 @@ def main():
         ge.build()
     from cunet_b200.models.cu_net import create_cu_net
     from cunet_b200.engine import Trainer
-    from oracle import synthetic                       # synthetic inputs only
+    from cunet_b200.utils import synthetic
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -327,10 +327,19 @@ def main():
         clocks=sampler.summary(),
     )
     if not args.no_cpu_baseline and world == 1:
-        ips, cores = cpu_reference(cfg, args.cpu_sample, 2)
-        line["cpu_baseline"] = dict(value=ips, unit="images/s", cores=cores, kind="port",
-                                    sample="%d-image training step of the same model on the host, median of 2"
-                                           % args.cpu_sample)
+        # the reference arm in a child process: its thread settings stay out of this process and a pathological host
+        # (oversubscribed cores) can only cost a bounded amount of time
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                                  "--cpu-sample", str(args.cpu_sample), "--steps", "2"] +
+                                 (["--dtype", args.dtype] if args.dtype else []) +
+                                 (["--batch", str(args.batch)] if args.batch else []),
+                                 capture_output=True, text=True, timeout=240).stdout
+            ref = json.loads(out.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as exc:  # noqa: BLE001 -- report, never fail the GPU line because of the CPU baseline
+            line["cpu_baseline"] = dict(value=None, unit="images/s", cores=None, kind="port",
+                                        sample="unavailable: %s" % type(exc).__name__)
     print(json.dumps(line))
     return 0
 

@@ -110,8 +110,7 @@ def run(opt, loader=None):
         import torch.distributed as dist
         dist.broadcast(eng.params, 0)
     if loader is None:
-        sys.path.insert(0, ROOT)
-        from oracle import synthetic             # synthetic batches only
+        from cunet_b200.utils import synthetic   # seeded synthetic batches
 
         def loader_fn(epoch):
             for it in range(opt.iters_per_epoch):

@@ -8,5 +8,6 @@ Layout
   models/      drop-in for the reference's models/cu_net.py  (create_cu_net)
   utils/       drop-in for utils/quantize.py (QuanOp), BinOp
   pylib/       drop-in for pylib/Evaluation.get_preds
+  utils/synthetic.py  seeded synthetic batches for cu-net.py / bench.py
 """
 __version__ = "0.1.0"

@@ -158,3 +158,11 @@ def test_get_preds_semantics():
     img, hm = synthetic.make_inputs(2, 5, seed=1)
     p = evaluation_oracle.get_preds(hm)
     assert (p >= 5).all() and (p <= 60).all()
+
+
+def test_product_synthetic_matches_oracle_copy():
+    """cu-net.py / bench.py generate their batches with cunet_b200.utils.synthetic; the oracle keeps its own copy."""
+    from cunet_b200.utils import synthetic as prod
+    for seed in (0, 7):
+        a, b = prod.make_inputs(2, 5, seed=seed), synthetic.make_inputs(2, 5, seed=seed)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
