@@ -59,6 +59,8 @@ def parse(argv=None):
                     help="bin: BinOp protocol (cu-net-prev-version-bin.py); quan: QuanOp (…-wig.py)")
     ap.add_argument("--data", choices=["synthetic"], default="synthetic")
     ap.add_argument("--iters_per_epoch", type=int, default=20)
+    ap.add_argument("--save_freq", type=int, default=0,
+                    help="write <exp_dir>/<exp_id>/lr-<lr>-<epoch>.pth.tar (the reference's checkpoint format) every n epochs")
     ap.add_argument("--fused", dest="fused", action="store_true", default=True)
     ap.add_argument("--no-fused", dest="fused", action="store_false")
     opt = ap.parse_args(argv)
@@ -74,6 +76,37 @@ def adjust_lr(opt, epoch):
     elif epoch in (141, 161):
         opt.lr *= 0.5
     return opt.lr
+
+
+class TrainHistory(object):
+    """What utils/checkpoint.py reads and writes of the reference's TrainHistory: the lr / epoch records."""
+
+    def __init__(self, lr=0.0):
+        self.lr, self.epoch, self.is_best = [{"lr": lr}], [{"epoch": -1}], False
+
+    def update(self, lr, epoch):
+        self.lr.append({"lr": lr})
+        self.epoch.append({"epoch": epoch})
+
+    def state_dict(self):
+        return {"lr": self.lr, "epoch": self.epoch}
+
+    def load_state_dict(self, sd):
+        self.lr, self.epoch = list(sd["lr"]), list(sd["epoch"])
+
+
+def resume(net, opt, history):
+    """--resume_prefix: load <exp_dir>/<exp_id>/<resume_prefix>[.pth.tar] (written by this script or by the reference,
+    cu-net.py:63-73) into the network by name.  Returns the checkpoint's optimizer state (or None)."""
+    import torch
+    from cunet_b200.utils.checkpoint import Checkpoint
+    ck = Checkpoint()
+    stem = os.path.join(opt.exp_dir, opt.exp_id, opt.resume_prefix)
+    ck.load_prefix = stem[:-len(".pth.tar")] if stem.endswith(".pth.tar") else stem
+    if not ck.load_checkpoint(net, None, history):
+        raise IOError("--resume_prefix: no checkpoint at %s.pth.tar" % ck.load_prefix)
+    opt.lr = history.lr[-1]["lr"]
+    return torch.load(ck.load_prefix + ".pth.tar", map_location="cpu", weights_only=False).get("optimizer")
 
 
 def run(opt, loader=None):
@@ -98,6 +131,8 @@ def run(opt, loader=None):
     torch.manual_seed(0)
     net = create_cu_net(neck_size=4, growth_rate=32, init_chan_num=128, class_num=opt.class_num,
                         layer_num=opt.layer_num, order=opt.order, loss_num=opt.loss_num, dtype=opt.dtype)
+    history = TrainHistory(opt.lr)
+    opt_state = resume(net, opt, history) if opt.resume_prefix else None     # host-side, before the weights move to HBM
     bs = max(1, opt.bs // world)              # the reference's DataParallel splits --bs over the GPUs (cu-net.py:59,84)
     eng = net.engine(bs, dev)
     quant = None
@@ -106,6 +141,9 @@ def run(opt, loader=None):
     elif opt.quant == "quan":
         quant = QuanOp(net, bits_w=opt.bits_w, bits_g=opt.bits_g)
     tr = Trainer(net, bs, lr=opt.lr, device=dev, process_group=pg, world_size=world, quant=quant)
+    if opt_state is not None and opt_state.get("state"):
+        from cunet_b200.utils.checkpoint import rmsprop_state_to_flat
+        rmsprop_state_to_flat(net, opt_state, eng)
     if world > 1:
         import torch.distributed as dist
         dist.broadcast(eng.params, 0)
@@ -118,7 +156,7 @@ def run(opt, loader=None):
     else:
         def loader_fn(epoch):
             return iter(loader)
-    history = []
+    losses = []
     if not opt.is_train:
         net.eval()
         losses = []
@@ -136,7 +174,7 @@ def run(opt, loader=None):
     opt_torch = None
     if not opt.fused:
         opt_torch = torch.optim.RMSprop(net.parameters(), lr=opt.lr, alpha=0.99, eps=1e-8, momentum=0, weight_decay=0)
-    for epoch in range(opt.nEpochs):
+    for epoch in range(history.epoch[-1]["epoch"] + 1, opt.nEpochs):
         if opt.adjust_lr:
             tr.set_lr(adjust_lr(opt, epoch))
         t0, n_img, last = time.time(), 0, 0.0
@@ -156,10 +194,18 @@ def run(opt, loader=None):
             n_img += img.shape[0] * world
             if rank == 0 and (i % opt.print_freq == 0):
                 print("epoch %d iter %d loss %.6f" % (epoch, i, last))
-        history.append(last)
+        losses.append(last)
+        history.update(opt.lr, epoch)
         if rank == 0:
             print("epoch %d done: loss %.6f, %.1f images/s" % (epoch, last, n_img / (time.time() - t0)))
-    return history
+            if opt.save_freq > 0 and (epoch + 1) % opt.save_freq == 0:
+                from cunet_b200.utils.checkpoint import Checkpoint, rmsprop_state_from_flat
+                ck = Checkpoint()
+                os.makedirs(os.path.join(opt.exp_dir, opt.exp_id), exist_ok=True)
+                ck.save_prefix = os.path.join(opt.exp_dir, opt.exp_id) + os.sep
+                state = opt_torch.state_dict() if opt_torch is not None else rmsprop_state_from_flat(net, eng, opt.lr)
+                ck.save_checkpoint(net, state, history)
+    return losses
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ Layout
   plan.py      static op plan of the network (virtual-concat segment tables, buffers, schedules)
   engine.py    executes a plan through the C ABI (forward, backward, fused train step)
   models/      drop-in for the reference's models/cu_net.py  (create_cu_net)
-  utils/       drop-in for utils/quantize.py (QuanOp), BinOp
+  utils/       drop-ins for utils/quantize.py (QuanOp), BinOp and utils/checkpoint.py (Checkpoint)
   pylib/       drop-in for pylib/Evaluation.get_preds
   utils/synthetic.py  seeded synthetic batches for cu-net.py / bench.py
 """

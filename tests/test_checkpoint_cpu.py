@@ -1,0 +1,116 @@
+"""Checkpoint compatibility with the reference (utils/checkpoint.py:40-67), host logic only (no GPU):
+the parameter tree of cunet_b200's CUNetB200 carries the reference's names and NCHW shapes, so a state_dict written
+by the reference's DataParallel-wrapped net loads by name, and files written here load in the reference."""
+import os
+
+import pytest
+import torch
+
+from oracle import ref_loader
+
+
+class _History(object):
+    """Minimal stand-in for utils/train_history.TrainHistory: what Checkpoint touches."""
+    def __init__(self, lr=2.5e-4, epoch=3):
+        self.lr, self.epoch, self.is_best = [{"lr": lr}], [{"epoch": epoch}], True
+
+    def state_dict(self):
+        return {"lr": self.lr, "epoch": self.epoch}
+
+    def load_state_dict(self, sd):
+        self.lr, self.epoch = sd["lr"], sd["epoch"]
+
+
+def _nets(class_num=5, layer_num=3, order=1, loss_num=2):
+    from cunet_b200.models.cu_net import create_cu_net
+    ours = create_cu_net(4, 32, 128, class_num, layer_num, order, loss_num)
+    ref = ref_loader.create_reference_net(class_num, layer_num, order, loss_num)
+    return ours, ref
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_reference_checkpoint_loads_by_name(tmp_path):
+    from cunet_b200.utils.checkpoint import Checkpoint
+    ours, ref = _nets()
+    ref_sd = ref.state_dict()
+    assert list(ref_sd.keys()) == list(ours.state_dict().keys())          # names and registration order
+    # what the reference writes: DataParallel-prefixed keys + RMSprop state (cu-net.py:59-61, utils/checkpoint.py:16-19)
+    torch.manual_seed(1)
+    for v in ref_sd.values():
+        if v.dtype.is_floating_point:
+            v.copy_(torch.randn_like(v))
+    opt = torch.optim.RMSprop(ref.parameters(), lr=1e-3, alpha=0.99, eps=1e-8)
+    path = str(tmp_path / "lr-0.001-7")
+    torch.save({"train_history": {"lr": [{"lr": 1e-3}], "epoch": [{"epoch": 7}]},
+                "state_dict": {"module." + k: v for k, v in ref_sd.items()},
+                "optimizer": opt.state_dict()}, path + ".pth.tar")
+    ck = Checkpoint()
+    ck.load_prefix = path
+    hist = _History()
+    assert ck.load_checkpoint(ours, None, hist)
+    assert hist.epoch[-1]["epoch"] == 7
+    for k, v in ours.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_our_checkpoint_loads_in_the_reference(tmp_path):
+    from cunet_b200.utils.checkpoint import Checkpoint
+    ours, ref = _nets()
+    ck = Checkpoint()
+    ck.save_prefix = str(tmp_path) + os.sep
+    opt = torch.optim.RMSprop(ours.parameters(), lr=2.5e-4, alpha=0.99, eps=1e-8)
+    path = ck.save_checkpoint(ours, opt, _History(2.5e-4, 3))
+    assert path.endswith("lr-0.00025-3.pth.tar") and os.path.isfile(path[:-8] + "-model-best.pth.tar")
+    saved = torch.load(path, weights_only=False)
+    assert all(k.startswith("module.") for k in saved["state_dict"])
+    # the reference's own loop (utils/checkpoint.py:53-61) on its DataParallel-named dict
+    net_dict = {"module." + k: v for k, v in ref.state_dict().items()}
+    for name, param in saved["state_dict"].items():
+        assert name in net_dict, name
+        net_dict[name].copy_(param)
+    for k, v in ours.state_dict().items():
+        assert torch.equal(ref.state_dict()[k], v), k
+
+
+def test_old_checkpoints_without_num_batches_tracked(tmp_path):
+    from cunet_b200.models.cu_net import create_cu_net
+    from cunet_b200.utils.checkpoint import load_weights
+    a = create_cu_net(4, 32, 128, 3, 2, 1, 2)
+    b = create_cu_net(4, 32, 128, 3, 2, 1, 2)
+    sd = {"module." + k: v for k, v in a.state_dict().items() if not k.endswith("num_batches_tracked")}
+    sd["module.not_in_net.weight"] = torch.zeros(1)
+    loaded, skipped, missing = load_weights(b, sd)
+    assert skipped == ["not_in_net.weight"] and all(m.endswith("num_batches_tracked") for m in missing)
+    for k, v in b.state_dict().items():
+        if not k.endswith("num_batches_tracked"):
+            assert torch.equal(v, a.state_dict()[k]), k
+    with pytest.raises(ValueError):
+        load_weights(b, {"features.conv0.weight": torch.zeros(2, 2)})
+
+
+def test_entry_point_resume(tmp_path):
+    """cu-net.py --resume_prefix: weights, lr and epoch come back from a checkpoint in the reference's format."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("cu_net_entry", os.path.join(root, "cu-net.py"))
+    entry = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(entry)
+    from cunet_b200.models.cu_net import create_cu_net
+    from cunet_b200.utils.checkpoint import Checkpoint
+    a = create_cu_net(4, 32, 128, 3, 2, 1, 2)
+    hist = entry.TrainHistory(1e-3)
+    hist.update(5e-4, 11)
+    os.makedirs(str(tmp_path / "run1"))
+    ck = Checkpoint()
+    ck.save_prefix = str(tmp_path / "run1") + os.sep
+    opt_a = torch.optim.RMSprop(a.parameters(), lr=5e-4)
+    path = ck.save_checkpoint(a, opt_a, hist)
+    opt = entry.parse(["--exp_dir", str(tmp_path), "--exp_id", "run1", "--layer_num", "2", "--class_num", "3",
+                       "--resume_prefix", os.path.basename(path)])
+    b = create_cu_net(4, 32, 128, 3, 2, 1, 2)
+    hist_b = entry.TrainHistory(opt.lr)
+    state = entry.resume(b, opt, hist_b)
+    assert opt.lr == 5e-4 and hist_b.epoch[-1]["epoch"] == 11 and "param_groups" in state
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, a.state_dict()[k]), k
