@@ -59,6 +59,8 @@ def parse(argv=None):
                     help="bin: BinOp protocol (cu-net-prev-version-bin.py); quan: QuanOp (…-wig.py)")
     ap.add_argument("--data", choices=["synthetic"], default="synthetic")
     ap.add_argument("--iters_per_epoch", type=int, default=20)
+    ap.add_argument("--flip_test", type=str2bool, default=False,
+                    help="validation with the reference's flip test-time augmentation and heat-map PCK (cu-net.py:240-254)")
     ap.add_argument("--save_freq", type=int, default=0,
                     help="write <exp_dir>/<exp_id>/lr-<lr>-<epoch>.pth.tar (the reference's checkpoint format) every n epochs")
     ap.add_argument("--fused", dest="fused", action="store_true", default=True)
@@ -162,13 +164,21 @@ def run(opt, loader=None):
         losses = []
         if quant is not None:
             (quant.binarization if opt.quant == "bin" else quant.quantization)()
+        pck = []
+        idx = [0, 1, 2, 3, 4, 5, 10, 11, 14, 15]                  # cu-net.py:127
         for img, hm in loader_fn(0):
-            loss, preds = tr.eval_step(img.to(dev), hm.to(dev))
+            if opt.flip_test:
+                from cunet_b200.pylib import Evaluation
+                loss, preds, avg = tr.eval_step_flip(img.to(dev), hm.to(dev))
+                pck.append(float(Evaluation.accuracy(avg, hm.to(dev), [i for i in idx if i < opt.class_num])[0]))
+            else:
+                loss, preds = tr.eval_step(img.to(dev), hm.to(dev))
             losses.append(float(loss))
         if quant is not None:
             quant.restore()
         if rank == 0:
-            print("val loss %.6f" % (sum(losses) / max(1, len(losses))))
+            print("val loss %.6f" % (sum(losses) / max(1, len(losses))) +
+                  (", pck %.4f" % (sum(pck) / len(pck)) if pck else ""))
         return losses
     net.train()
     opt_torch = None

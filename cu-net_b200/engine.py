@@ -519,6 +519,32 @@ class Trainer(object):
             e.optimizer_step(self.alpha, self.eps)
         return e.loss_value()
 
+    def eval_step_flip(self, img=None, heatmap=None, flip_index=None):
+        """validate() of the reference with its flip test-time augmentation (cu-net.py:225-249), without leaving the
+        GPU: forward, multi-loss MSE of the un-flipped pass (:235-238), forward of the width-flipped image (:240-245),
+        flip the last head back + swap the left/right channels (:246-247), average (:248), decode.
+        Returns (loss, preds [N,C,2] of the averaged map, averaged map [N,C,H,W])."""
+        from .pylib import Evaluation, HumanAug
+        e = self.eng
+        if img is not None:
+            self.load_batch(img, heatmap)
+        if flip_index is None:
+            if e.plan.class_num != 16:
+                raise ValueError("flip_index is required unless class_num == 16 (MPII pairs, cu-net.py:32-33)")
+            flip_index = HumanAug.MPII_FLIP_INDEX
+        e.forward(train=False)
+        e.loss_and_decode(with_grad=False)
+        loss = e.loss_value()
+        out1 = e.head_outputs()[-1].float().clone()
+        orig = e.img.clone()
+        e.img.copy_(torch.flip(orig, dims=[3]))
+        e.forward(train=False)
+        out2 = HumanAug.shuffle_channels_for_horizontal_flipping(HumanAug.flip_channels(e.head_outputs()[-1]),
+                                                                 flip_index)
+        e.img.copy_(orig)
+        avg = ((out1 + out2) / 2).contiguous()
+        return loss, Evaluation.get_preds(avg), avg
+
     def eval_step(self, img=None, heatmap=None):
         e = self.eng
         if img is not None:

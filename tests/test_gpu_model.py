@@ -167,3 +167,25 @@ def test_bf16_forward_backward_tolerance():
     assert abs(float(loss.detach()) - float(oloss.detach())) / abs(float(oloss.detach())) < 1e-2
     for name, p in net.named_parameters():
         assert torch.isfinite(p.grad).all(), name
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet executed on a B200")
+def test_flip_tta_eval_step_matches_oracle():
+    """Trainer.eval_step_flip == validate() of cu-net.py:225-249 computed with the oracle on the CPU (eval-mode BN)."""
+    from cunet_b200.engine import Trainer
+    from cunet_b200.pylib import HumanAug
+    class_num, L, K, loss_num, n = 16, 2, 1, 2, 2
+    net, ora, img, hm = _setup(class_num, L, K, loss_num, n, "fp32")
+    net.eval()
+    ora.eval()
+    tr = Trainer(net, n, device="cuda:0")
+    loss, preds, avg = tr.eval_step_flip(img.cuda(), hm.cuda())
+    with torch.no_grad():
+        o1 = ora(img)
+        o2 = ora(torch.flip(img, dims=[3]))
+        want = (o1[-1] + evaluation_oracle.shuffle_channels_for_horizontal_flipping(
+            evaluation_oracle.flip_channels(o2[-1]), HumanAug.MPII_FLIP_INDEX)) / 2
+        oloss = cunet_oracle.multi_loss_mse(o1, hm)
+    assert _rel(avg.cpu(), want) < 1e-3
+    assert abs(float(loss) - float(oloss)) < 1e-3 * abs(float(oloss))
+    assert torch.equal(preds.cpu(), evaluation_oracle.get_preds(avg.cpu()))
