@@ -63,7 +63,6 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
   const int st0 = (int)blockIdx.x * per, st1 = min(total, st0 + per);
   const int ldo = p.dy.ld * 2;
   const int dTn = 1 + (p.dy.mode == 1 ? 1 : 0) + (p.dy.pooled ? 1 : 0);
-  const int njobs = dTn + p.in.nseg;  // landing jobs per stage
   int need_low = p.dy.pooled;
   for (int s = 0; s < p.in.nseg; ++s) need_low |= p.in.seg[s].up;
 
