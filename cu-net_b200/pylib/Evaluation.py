@@ -70,3 +70,74 @@ def accuracy(output, target, idxs, thr=0.5):
     """PCK on the heat maps (pylib/Evaluation.py:55-85): both decodes run the fused CUDA kernel; acc[0] is the mean over
     ``idxs`` of the per-joint accuracies that have at least one valid target."""
     return accuracy_from_preds(get_preds(output), get_preds(target), output.shape[3], idxs, thr)
+
+
+MPII_PCKH_JOINTS = (0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15)     # pylib/Evaluation.py:92
+
+
+def inverse_crop_transforms(center, scale, rot, res, size=200):
+    """Batched inverse of pylib/HumanAug.py:10-34 (GetTransform): [N,3,3] float64 on the inputs' device."""
+    center, scale, rot = center.double(), scale.double().reshape(-1), rot.double().reshape(-1)
+    n = center.shape[0]
+    h = size * scale
+    t = torch.zeros(n, 3, 3, dtype=torch.float64, device=center.device)
+    t[:, 0, 0] = res / h
+    t[:, 1, 1] = res / h
+    t[:, 0, 2] = res * (-center[:, 0] / h + 0.5)
+    t[:, 1, 2] = res * (-center[:, 1] / h + 0.5)
+    t[:, 2, 2] = 1
+    rad = -rot * (torch.pi / 180)                      # "to match direction of rotation from cropping"
+    sn, cs = torch.sin(rad), torch.cos(rad)
+    rm = torch.zeros_like(t)
+    rm[:, 0, 0], rm[:, 0, 1], rm[:, 1, 0], rm[:, 1, 1], rm[:, 2, 2] = cs, -sn, sn, cs, 1
+    tm = torch.eye(3, dtype=torch.float64, device=center.device).repeat(n, 1, 1)
+    tm[:, 0, 2] = -res / 2
+    tm[:, 1, 2] = -res / 2
+    ti = tm.clone()
+    ti[:, :2, 2] *= -1
+    return torch.linalg.inv(ti @ rm @ tm @ t)          # rot == 0: the rotation factors cancel to the identity
+
+
+def final_preds_from_coords(output, coords, center, scale, res, rot):
+    """The arithmetic of ``final_preds`` after the decode (device-agnostic, no per-joint Python loop):
+    quarter-pixel refinement (pylib/Evaluation.py:113-121), +0.5, inverse crop transform, truncation to int (:134-150)."""
+    n, c, hh, ww = output.shape
+    coords = coords.float().clone()
+    px = torch.floor(coords[..., 0]).long()
+    py = torch.floor(coords[..., 1]).long()
+    ok = (px > 1) & (px < res[0]) & (py > 1) & (py < res[1])
+    flat = output.reshape(n, c, hh * ww).float()
+
+    def at(y, x):
+        idx = (y.clamp(0, hh - 1) * ww + x.clamp(0, ww - 1)).unsqueeze(-1)
+        return flat.gather(2, idx).squeeze(-1)
+    dx = at(py - 1, px) - at(py - 1, px - 2)
+    dy = at(py, px - 1) - at(py - 2, px - 1)
+    step = torch.stack([torch.sign(dx), torch.sign(dy)], -1) * 0.25
+    coords = coords + torch.where(ok.unsqueeze(-1), step, torch.zeros_like(step)) + 0.5
+    tinv = inverse_crop_transforms(center, scale, rot, res[0])
+    homog = torch.cat([coords.double(), torch.ones(n, c, 1, dtype=torch.float64, device=coords.device)], -1)
+    out = torch.einsum("nij,ncj->nci", tinv, homog)[..., :2]
+    return torch.trunc(out).float()
+
+
+def final_preds(output, center, scale, res, rot):
+    """pylib/Evaluation.py:108-132: landmark predictions in original-image coordinates (decode on the GPU)."""
+    dev = output.device
+    return final_preds_from_coords(output, get_preds(output), center.to(dev), scale.to(dev), res, rot.to(dev))
+
+
+def accuracy_origin_res(output, center, scale, res, grnd_pts, normalizers, rot):
+    """pylib/Evaluation.py:88-106: PCKh at the original resolution over the 14 MPII joints."""
+    dev = output.device
+    pred = final_preds(output, center, scale, res, rot)
+    dists = calc_dists(pred, grnd_pts.to(dev), normalizers.to(dev), use_zero=True)
+    acc = torch.zeros(len(MPII_PCKH_JOINTS) + 1, device=dev)
+    avg, cnt = 0.0, 0
+    for i, cidx in enumerate(MPII_PCKH_JOINTS):
+        acc[i + 1] = dist_acc(dists[cidx])
+        if float(acc[i + 1]) >= 0:
+            avg, cnt = avg + float(acc[i + 1]), cnt + 1
+    if cnt:
+        acc[0] = avg / cnt
+    return acc

@@ -3,6 +3,9 @@
 TEST INFRASTRUCTURE -- see oracle/__init__.py.  The reference file cannot be imported
 (``import HumanAug`` is a python-2 implicit relative import), so ``get_preds`` is restated.
 """
+import math
+
+import numpy as np
 import torch
 
 
@@ -74,3 +77,77 @@ def shuffle_channels_for_horizontal_flipping(maps, flip_indxs):
         maps.narrow(dim, idx1, 1).copy_(maps.narrow(dim, idx2, 1))
         maps.narrow(dim, idx2, 1).copy_(tmp)
     return maps
+
+
+def get_transform(center, scale, rot, res, size):
+    """pylib/HumanAug.py:10-34 (GetTransform)."""
+    h = size * scale
+    t = np.zeros((3, 3))
+    t[0, 0] = float(res) / h
+    t[1, 1] = float(res) / h
+    t[0, 2] = res * (-float(center[0]) / h + .5)
+    t[1, 2] = res * (-float(center[1]) / h + .5)
+    t[2, 2] = 1
+    if not rot == 0:
+        rot = -rot
+        rot_mat = np.zeros((3, 3))
+        rot_rad = rot * np.pi / 180
+        sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+        rot_mat[0, :2] = [cs, -sn]
+        rot_mat[1, :2] = [sn, cs]
+        rot_mat[2, 2] = 1
+        t_mat = np.eye(3)
+        t_mat[0, 2] = -res / 2
+        t_mat[1, 2] = -res / 2
+        t_inv = t_mat.copy()
+        t_inv[:2, 2] *= -1
+        t = np.dot(t_inv, np.dot(rot_mat, np.dot(t_mat, t)))
+    return t
+
+
+def transform_pts(pts, center, scale, rot, res, size, invert=0):
+    """pylib/HumanAug.py:44-52 (TransformPts)."""
+    nlmk = pts.shape[0]
+    t = get_transform(center, scale, rot, res, size)
+    if invert:
+        t = np.linalg.inv(t)
+    new_pt = np.concatenate((pts, np.ones((nlmk, 1))), axis=1).T
+    new_pt = np.dot(t, new_pt)
+    return new_pt[0:2, :].T.astype(int)
+
+
+def final_preds(output, center, scale, res, rot):
+    """pylib/Evaluation.py:108-132 + transform_preds :134-150: quarter-pixel refinement towards the higher
+    neighbour, +0.5, inverse crop transform (size 200), truncation to int."""
+    coords = get_preds(output)
+    for n in range(coords.size(0)):
+        for p in range(coords.size(1)):
+            hm = output[n][p]
+            px = int(math.floor(coords[n][p][0]))
+            py = int(math.floor(coords[n][p][1]))
+            if px > 1 and px < res[0] and py > 1 and py < res[1]:
+                diff = torch.Tensor([hm[py - 1][px] - hm[py - 1][px - 2], hm[py][px - 1] - hm[py - 2][px - 1]])
+                coords[n][p] += diff.sign() * .25
+    coords += 0.5
+    preds = coords.clone()
+    for i in range(coords.size(0)):
+        preds[i] = torch.from_numpy(transform_pts(coords[i].numpy(), center[i].numpy(), scale[i].numpy(),
+                                                  rot[i].numpy(), res[0], size=200, invert=1))
+    return preds
+
+
+def accuracy_origin_res(output, center, scale, res, grnd_pts, normalizers, rot):
+    """pylib/Evaluation.py:88-106 (PCKh at the original resolution, the 14 MPII joints of :92)."""
+    idxs = [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15]
+    pred_pts = final_preds(output, center, scale, res, rot)
+    dists = calc_dists(pred_pts, grnd_pts, normalizers, use_zero=True)
+    acc = torch.zeros(len(idxs) + 1)
+    avg_acc, cnt = 0, 0
+    for i in range(len(idxs)):
+        acc[i + 1] = dist_acc(dists[idxs[i]])
+        if acc[i + 1] >= 0:
+            avg_acc = avg_acc + acc[i + 1]
+            cnt += 1
+    if cnt != 0:
+        acc[0] = avg_acc / cnt
+    return acc

@@ -35,3 +35,29 @@ def test_accuracy_arithmetic_matches_reference_loops():
     assert (d_ref == -1).any() and (d_ref > 0).any()
     # all-invalid joint
     assert float(Evaluation.dist_acc(torch.full((4,), -1.0))) == -1.0
+
+
+def test_final_preds_arithmetic_matches_reference_loops():
+    """Quarter-pixel refinement + inverse crop transform (with and without rotation) against the reference's loops."""
+    from cunet_b200.pylib import Evaluation
+    n, c = 4, 16
+    _, target = synthetic.make_inputs(n, c, seed=9)
+    g = torch.Generator().manual_seed(2)
+    output = target + 0.05 * torch.randn(target.shape, generator=g)
+    output[1, 2] = 0.0
+    output[1, 2, 0, 5] = 1.0                                           # a peak on the border: no refinement
+    center = torch.rand(n, 2, generator=g) * 400 + 300
+    scale = torch.rand(n, generator=g) * 2 + 0.8
+    rot = torch.tensor([0.0, 25.0, -40.0, 0.0])
+    res = [64, 64]
+    want = evaluation_oracle.final_preds(output.clone(), center, scale, res, rot)
+    got = Evaluation.final_preds_from_coords(output, evaluation_oracle.get_preds(output), center, scale, res, rot)
+    # truncation to int: allow a 1-pixel difference only where the float result sits within 1e-6 of an integer
+    assert (got - want).abs().max() <= 1.0
+    assert ((got - want).abs() > 0).float().mean() < 0.01
+    # PCKh arithmetic on top of it
+    grnd = want + torch.randint(-6, 7, want.shape, generator=g).float()
+    grnd[0, 3] = 0.0                                                   # missing joint
+    norm = torch.rand(n, generator=g) * 20 + 40
+    d_ref = evaluation_oracle.calc_dists(want, grnd, norm, use_zero=True)
+    assert torch.allclose(Evaluation.calc_dists(want, grnd, norm, use_zero=True), d_ref, atol=1e-6)
