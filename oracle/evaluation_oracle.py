@@ -151,3 +151,35 @@ def accuracy_origin_res(output, center, scale, res, grnd_pts, normalizers, rot):
     if cnt != 0:
         acc[0] = avg_acc / cnt
     return acc
+
+
+def draw_gaussian(img, pt, sigma):
+    """pylib/HumanPts.py:50-76 (numpy, in place)."""
+    tmp_size = np.ceil(3 * sigma)
+    ul = [int(pt[0] - tmp_size), int(pt[1] - tmp_size)]
+    br = [int(pt[0] + tmp_size), int(pt[1] + tmp_size)]
+    if (ul[0] >= img.shape[1] or ul[1] >= img.shape[0] or br[0] < 0 or br[1] < 0):
+        return img
+    size = 2 * tmp_size + 1
+    x = np.arange(0, size, 1, float)
+    y = x[:, np.newaxis]
+    x0 = y0 = size // 2
+    g = np.exp(- ((x - x0) ** 2 + (y - y0) ** 2) / (tmp_size ** 2))
+    g_x = max(0, -ul[0]), min(br[0] + 1, img.shape[1]) - max(0, ul[0]) + max(0, -ul[0])
+    g_y = max(0, -ul[1]), min(br[1] + 1, img.shape[0]) - max(0, ul[1]) + max(0, -ul[1])
+    img_x = max(0, ul[0]), min(br[0] + 1, img.shape[1])
+    img_y = max(0, ul[1]), min(br[1] + 1, img.shape[0])
+    img[img_y[0]:img_y[1], img_x[0]:img_x[1]] = g[g_y[0]:g_y[1], g_x[0]:g_x[1]]
+    return img
+
+
+def pts2heatmap(pts, heatmap_shape, sigma=1):
+    """pylib/HumanPts.py:35-48."""
+    heatmap = np.zeros((pts.shape[0], heatmap_shape[0], heatmap_shape[1]))
+    valid_pts = np.zeros((pts.shape))
+    for i in range(0, pts.shape[0]):
+        if pts[i][0] <= 0 or pts[i][1] <= 0:
+            continue
+        heatmap[i] = draw_gaussian(heatmap[i], pts[i], sigma)
+        valid_pts[i] = pts[i]
+    return heatmap, valid_pts

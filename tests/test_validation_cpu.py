@@ -61,3 +61,27 @@ def test_final_preds_arithmetic_matches_reference_loops():
     norm = torch.rand(n, generator=g) * 20 + 40
     d_ref = evaluation_oracle.calc_dists(want, grnd, norm, use_zero=True)
     assert torch.allclose(Evaluation.calc_dists(want, grnd, norm, use_zero=True), d_ref, atol=1e-6)
+
+
+def test_pts2heatmap_matches_reference_drawing():
+    """Batched target heat maps == the reference's per-landmark numpy drawing, including clipped windows, the
+    truncation quirk next to the top/left border, landmarks outside the map and missing (<= 0) landmarks."""
+    import numpy as np
+    from cunet_b200.pylib import HumanPts
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand(3, 16, 2, generator=g) * 70 - 3            # some outside [0, 64), some negative
+    pts[0, 0] = torch.tensor([2.5, 30.2])                        # pt - 3 in (-1, 0): int() truncates to 0
+    pts[0, 1] = torch.tensor([63.9, 0.4])
+    pts[0, 2] = torch.tensor([10.0, 12.0])                       # integer landmark (the synthetic inputs)
+    pts[0, 3] = torch.tensor([66.2, 20.0])                       # window partly inside from the right
+    pts[0, 4] = torch.tensor([80.0, 20.0])                       # entirely outside
+    got, valid = HumanPts.pts2heatmap(pts, (64, 64), sigma=1)
+    for n in range(3):
+        want, wvalid = evaluation_oracle.pts2heatmap(pts[n].numpy().astype(np.float64), (64, 64), 1)
+        assert np.abs(got[n].numpy() - want).max() < 1e-6, n
+        assert np.abs(valid[n].numpy() - wvalid).max() < 1e-6
+    # the synthetic heat maps of the bench are this drawing at integer landmarks
+    assert float(got[0, 2].max()) == 1.0 and int(got[0, 2].argmax()) == 12 * 64 + 10
+    # and heatmap2pts inverts it up to the reference's (x, y + 0.5) convention
+    back = HumanPts.heatmap2pts(got[:1, 2:3])
+    assert back.tolist() == [[[10.0, 12.5]]]
