@@ -7,7 +7,7 @@ Layout
   engine.py    executes a plan through the C ABI (forward, backward, fused train step)
   models/      drop-in for the reference's models/cu_net.py  (create_cu_net)
   utils/       drop-ins for utils/quantize.py (QuanOp), BinOp and utils/checkpoint.py (Checkpoint)
-  pylib/       drop-in for pylib/Evaluation.get_preds
+  pylib/       drop-ins for pylib/Evaluation (get_preds, accuracy, final_preds), HumanAug (flip helpers), HumanPts (heat maps)
   utils/synthetic.py  seeded synthetic batches for cu-net.py / bench.py
 """
 __version__ = "0.1.0"
