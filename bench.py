@@ -157,6 +157,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--dtype", default="", choices=["", "bf16", "fp32"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's batch per GPU (default); strong: the config's batch is the GLOBAL batch, "
+                         "split over the GPUs like the reference's DataParallel does with --bs (cu-net.py:59,84)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images in the CPU-baseline sample step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -171,6 +174,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if max(args.warmup, 0) < 3:
         args.warmup = 3
+    if args.scaling == "strong":
+        if cfg["batch"] % world:
+            raise SystemExit("--scaling strong needs the global batch %d to be divisible by %d GPUs" % (cfg["batch"], world))
+        cfg["batch"] //= world
     workload = "CU-Net-%d order %d loss %d, %d classes, 256x256 -> 64x64 heatmaps, per-GPU batch %d, %s, train step" % (
         cfg["layer_num"], cfg["order"], cfg["loss_num"], cfg["class_num"], cfg["batch"], cfg["dtype"])
 
@@ -181,7 +188,7 @@ def main():
         ips, cores = cpu_reference(cfg, args.cpu_sample, max(1, min(args.steps, 3)))
         line = dict(impl="reference", metric="images_per_sec", value=ips, unit="images/s", n_gpus=args.gpus,
                     steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 * args.cpu_sample / ips,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=workload),
                     cpu_baseline=dict(value=ips, unit="images/s", cores=cores, kind="port",
                                       sample="%d-image training step (fwd+MSE+bwd+RMSprop) of the same model, median of %d"
@@ -306,7 +313,7 @@ def main():
     tflops = value * train_gflop_img / 1e3
     line = dict(
         metric="images_per_sec", value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-        ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+        ms_per_step=ms_per_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
         dtype="bf16" if cfg["dtype"] == "bf16" else "f32(3xtf32)", data="synthetic",
         config=dict(workload=workload, global_batch=world * B, parallelism="dp%d" % world,
                     l2="working set (~%.1f GB of activations per step) far exceeds the 126 MB L2; no flush needed"
