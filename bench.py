@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- CU-Net training-step throughput on B200 (images/sec), with roofline and CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cunet8|cunet2|cunet16] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cunet8|cunet2|cunet16|cunet8bin] [--scaling weak|strong] [--impl reference]
 
 One JSON line on stdout (rank 0).  A "step" is one full training step of the reference's train() loop
 (cu-net.py:147-206) on one batch of synthetic input: forward, multi-loss MSE (+ fused landmark decode), backward,
@@ -27,6 +27,9 @@ CONFIGS = {
     "cunet8": dict(layer_num=8, order=1, loss_num=8, class_num=68, batch=24, dtype="bf16"),
     "cunet2": dict(layer_num=2, order=1, loss_num=2, class_num=68, batch=24, dtype="fp32"),
     "cunet16": dict(layer_num=16, order=1, loss_num=16, class_num=16, batch=16, dtype="bf16"),
+    # BASELINE.json configs[3]: binary weights through the BinOp protocol of cu-net-prev-version-bin.py:163-191
+    # (16 MPII joints, :48): binarize -> forward/backward -> restore -> fix gradients -> RMSprop, all inside the step
+    "cunet8bin": dict(layer_num=8, order=1, loss_num=8, class_num=16, batch=24, dtype="bf16", quant="bin"),
 }
 
 
@@ -178,12 +181,16 @@ def main():
         if cfg["batch"] % world:
             raise SystemExit("--scaling strong needs the global batch %d to be divisible by %d GPUs" % (cfg["batch"], world))
         cfg["batch"] //= world
-    workload = "CU-Net-%d order %d loss %d, %d classes, 256x256 -> 64x64 heatmaps, per-GPU batch %d, %s, train step" % (
-        cfg["layer_num"], cfg["order"], cfg["loss_num"], cfg["class_num"], cfg["batch"], cfg["dtype"])
+    workload = "CU-Net-%d order %d loss %d, %d classes, 256x256 -> 64x64 heatmaps, per-GPU batch %d, %s, train step%s" % (
+        cfg["layer_num"], cfg["order"], cfg["loss_num"], cfg["class_num"], cfg["batch"], cfg["dtype"],
+        ", binary weights (BinOp protocol)" if cfg.get("quant") == "bin" else "")
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
+            return 0
+        if cfg.get("quant"):
+            print(json.dumps(dict(impl="reference", unavailable="the CPU reference arm times the full-precision step only")))
             return 0
         ips, cores = cpu_reference(cfg, args.cpu_sample, max(1, min(args.steps, 3)))
         line = dict(impl="reference", metric="images_per_sec", value=ips, unit="images/s", n_gpus=args.gpus,
@@ -217,7 +224,13 @@ def main():
     net = create_cu_net(4, 32, 128, cfg["class_num"], cfg["layer_num"], cfg["order"], cfg["loss_num"],
                         dtype=cfg["dtype"])
     B = cfg["batch"]
-    tr = Trainer(net, B, lr=2.5e-4, device=dev, process_group=pg, world_size=world, use_graph=not args.no_graph)
+    quant = None
+    if cfg.get("quant") == "bin":
+        from cunet_b200.utils.quantize import BinOp
+        net.engine(B, dev)                 # the quantizer needs the parameters in device storage
+        quant = BinOp(net)
+    tr = Trainer(net, B, lr=2.5e-4, device=dev, process_group=pg, world_size=world, use_graph=not args.no_graph,
+                 quant=quant)
     if world > 1:
         import torch.distributed as dist
         dist.broadcast(tr.eng.params, 0)
@@ -333,7 +346,7 @@ def main():
                         frac_of_bf16_sustained=tflops / pk["tf_sust"], peak_tflops=pk["tf_sust"]),
         clocks=sampler.summary(),
     )
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not cfg.get("quant"):
         # the reference arm in a child process: its thread settings stay out of this process and a pathological host
         # (oversubscribed cores) can only cost a bounded amount of time
         try:
