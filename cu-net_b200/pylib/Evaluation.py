@@ -100,7 +100,8 @@ def inverse_crop_transforms(center, scale, rot, res, size=200):
 
 def final_preds_from_coords(output, coords, center, scale, res, rot):
     """The arithmetic of ``final_preds`` after the decode (device-agnostic, no per-joint Python loop):
-    quarter-pixel refinement (pylib/Evaluation.py:113-121), +0.5, inverse crop transform, truncation to int (:134-150)."""
+    quarter-pixel refinement (pylib/Evaluation.py:113-121), +0.5, inverse crop transform of the 1-based points and
+    truncation to int (:134-150, :179-187)."""
     n, c, hh, ww = output.shape
     coords = coords.float().clone()
     px = torch.floor(coords[..., 0]).long()
@@ -116,9 +117,10 @@ def final_preds_from_coords(output, coords, center, scale, res, rot):
     step = torch.stack([torch.sign(dx), torch.sign(dy)], -1) * 0.25
     coords = coords + torch.where(ok.unsqueeze(-1), step, torch.zeros_like(step)) + 0.5
     tinv = inverse_crop_transforms(center, scale, rot, res[0])
-    homog = torch.cat([coords.double(), torch.ones(n, c, 1, dtype=torch.float64, device=coords.device)], -1)
+    # Evaluation.py's own TransformPts (:179-187) treats the points as 1-based: pts - 1 in, int() + 1 out
+    homog = torch.cat([coords.double() - 1, torch.ones(n, c, 1, dtype=torch.float64, device=coords.device)], -1)
     out = torch.einsum("nij,ncj->nci", tinv, homog)[..., :2]
-    return torch.trunc(out).float()
+    return (torch.trunc(out) + 1).float()
 
 
 def final_preds(output, center, scale, res, rot):

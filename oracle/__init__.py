@@ -11,7 +11,9 @@ Contents
 * ``cunet_oracle``     -- restatement of ``models/cu_net.py`` (functional, torch CPU fp32)
 * ``quantize_oracle``  -- restatement of ``utils/quantize.py`` (QuanOp, QuanInput) and of
                           ``models/cu_net_prev_version.py:17-92`` (BinOp)
-* ``evaluation_oracle``-- restatement of ``pylib/Evaluation.py:6-23`` (get_preds)
+* ``evaluation_oracle``-- restatement of ``pylib/Evaluation.py`` (get_preds, calc_dists, dist_acc, accuracy,
+                          final_preds + its own TransformPts, accuracy_origin_res), of the flip helpers of
+                          ``pylib/HumanAug.py:177-210`` and of ``pylib/HumanPts.py:35-76`` (pts2heatmap)
 * ``synthetic``        -- the seeded synthetic inputs of SURVEY.md §8(d)
 * ``ref_loader``       -- executes the *real* reference sources from /root/reference
                           (build container only; never on the GPU box)

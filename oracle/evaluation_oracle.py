@@ -80,7 +80,7 @@ def shuffle_channels_for_horizontal_flipping(maps, flip_indxs):
 
 
 def get_transform(center, scale, rot, res, size):
-    """pylib/HumanAug.py:10-34 (GetTransform)."""
+    """pylib/Evaluation.py:152-177 (GetTransform; identical to pylib/HumanAug.py:10-34)."""
     h = size * scale
     t = np.zeros((3, 3))
     t[0, 0] = float(res) / h
@@ -106,14 +106,15 @@ def get_transform(center, scale, rot, res, size):
 
 
 def transform_pts(pts, center, scale, rot, res, size, invert=0):
-    """pylib/HumanAug.py:44-52 (TransformPts)."""
+    """pylib/Evaluation.py:179-187 -- Evaluation.py's OWN TransformPts (1-based points: ``pts - 1`` in,
+    ``astype(int) + 1`` out), not the one of pylib/HumanAug.py:44-52 which lacks the two shifts."""
     nlmk = pts.shape[0]
     t = get_transform(center, scale, rot, res, size)
     if invert:
         t = np.linalg.inv(t)
-    new_pt = np.concatenate((pts, np.ones((nlmk, 1))), axis=1).T
+    new_pt = np.concatenate((pts - 1, np.ones((nlmk, 1))), axis=1).T
     new_pt = np.dot(t, new_pt)
-    return new_pt[0:2, :].T.astype(int)
+    return new_pt[0:2, :].T.astype(int) + 1
 
 
 def final_preds(output, center, scale, res, rot):

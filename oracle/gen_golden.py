@@ -117,8 +117,64 @@ def quant_case(name, bits_w, seed):
                 "num_targets": op.num_of_params}, os.path.join(OUT, name))
 
 
+def pylib_inputs(seed=11):
+    """Seeded inputs of the validation-path fixture (shared with tests/test_oracle_golden.py)."""
+    n, c = 3, 16
+    _, target = synthetic.make_inputs(n, c, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    output = target + 0.2 * torch.randn(target.shape, generator=g)
+    output[0, 3] = -1.0                      # no positive maximum: masked prediction
+    target[1, 4] = 0.0                       # missing ground-truth joint
+    output[2, 5] = 0.0
+    output[2, 5, 0, 7] = 1.0                 # peak on the border: no quarter-pixel refinement
+    center = torch.rand(n, 2, generator=g) * 400 + 300
+    scale = torch.rand(n, generator=g) * 2 + 0.8
+    rot = torch.tensor([0.0, 25.0, -40.0])
+    pts = torch.rand(n, c, 2, generator=g) * 70 - 3
+    pts[0, 0] = torch.tensor([2.5, 30.2])    # window start in (-1, 0): int() truncates towards zero
+    pts[0, 1] = torch.tensor([63.9, 0.4])
+    pts[0, 2] = torch.tensor([10.0, 12.0])
+    pts[0, 3] = torch.tensor([66.2, 20.0])   # window partly inside from the right
+    pts[0, 4] = torch.tensor([80.0, 20.0])   # entirely outside
+    grnd = torch.rand(n, c, 2, generator=g) * 900 + 50
+    grnd[0, 3] = 0.0
+    norm = torch.rand(n, generator=g) * 20 + 40
+    return dict(output=output, target=target, center=center, scale=scale, rot=rot, pts=pts, grnd_pts=grnd,
+                normalizers=norm, idxs=[0, 1, 2, 3, 4, 5, 10, 11, 14, 15],
+                flip_index=[[1, 4], [0, 5], [12, 13], [11, 14], [10, 15], [2, 3]])
+
+
+def pylib_case(name):
+    """Validation path + target heat maps: outputs of the REAL pylib/Evaluation.py, HumanAug.py, HumanPts.py."""
+    import numpy as np
+    mods = ref_loader.load_reference_pylib()
+    ev, aug, hp = mods["Evaluation"], mods["HumanAug"], mods["HumanPts"]
+    inp = pylib_inputs()
+    out, tgt = inp["output"], inp["target"]
+    res = [64, 64]
+    # the big inputs are NOT stored: tests regenerate them with pylib_inputs() and check this fingerprint
+    fx = dict(inputs_fingerprint=torch.stack([out.double().sum(), tgt.double().sum(), inp["pts"].double().sum()]),
+              small_inputs={k: inp[k] for k in ("center", "scale", "rot", "grnd_pts", "normalizers", "idxs", "flip_index")})
+    small = out[:2, :, 20:28, 20:28].contiguous()          # flip / shuffle are pure permutations: a crop pins them
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fx["get_preds"] = ev.get_preds(out.clone())
+        fx["accuracy"] = ev.accuracy(out.clone(), tgt.clone(), inp["idxs"])
+        fx["final_preds"] = ev.final_preds(out.clone(), inp["center"], inp["scale"], res, inp["rot"])
+        fx["accuracy_origin_res"] = ev.accuracy_origin_res(out.clone(), inp["center"], inp["scale"], res,
+                                                           inp["grnd_pts"], inp["normalizers"], inp["rot"])
+        fx["calc_dists"] = ev.calc_dists(fx["final_preds"], inp["grnd_pts"], inp["normalizers"], use_zero=True)
+        fx["flip_channels"] = aug.flip_channels(small.clone())
+        fx["shuffle"] = aug.shuffle_channels_for_horizontal_flipping(small.clone(), np.array(inp["flip_index"]))
+        h, v = hp.pts2heatmap(inp["pts"][0].numpy().astype(np.float64), (64, 64), 1)     # sample 0 holds the edge cases
+        fx["pts2heatmap"], fx["valid_pts"] = torch.from_numpy(h).float(), torch.from_numpy(v)
+        # hp.heatmap2pts is not executed: it relies on torch-0.1.12's keepdim=True result of torch.max (HumanPts.py:94,104)
+    torch.save(fx, os.path.join(OUT, name))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    pylib_case("pylib_eval.pt")
     tiny_case("tiny_L3_K2.pt", 3, 2, 2, 5, 2, 8, 16, seed=11)
     tiny_case("tiny_L2_K1.pt", 2, 1, 2, 3, 4, 8, 16, seed=12)
     tiny_case("tiny_L3_K0.pt", 3, 0, 3, 4, 2, 8, 16, seed=13)

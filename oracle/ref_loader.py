@@ -8,7 +8,14 @@ from running under python 3:
   * ``models/cu_net.py:286``  ``print '...'`` statement  -> function-call form
   * ``models/cu_net.py:94``   ``adapter_out_num / 2``    -> floor division
 Both are substituted in memory; nothing is copied into this repository.
+
+``pylib/HumanAug.py``, ``pylib/Evaluation.py`` and ``pylib/HumanPts.py`` (validation path and target heat maps) are
+python-2 sources as well: one ``print '...'`` statement each in a ``__main__`` block (HumanAug.py:277,
+HumanPts.py:336), tab/space mixed indentation in HumanPts.py:43-44 (python 2 counts a tab as eight columns) and the
+implicit relative ``import HumanAug`` of Evaluation.py:4.  ``load_reference_pylib`` executes them with those three
+things patched in memory.  None of the executed functions relies on python-2 integer division.
 """
+import re
 import contextlib
 import io
 import os
@@ -87,3 +94,43 @@ def load_reference_quantize(bits_w, bits_i=8, bits_g=8, exp_dir="/tmp/cunet_ref_
         for k, v in saved_mods.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def load_reference_pylib():
+    """Namespaces of the reference's pylib/HumanAug.py, pylib/Evaluation.py, pylib/HumanPts.py as module objects."""
+    if not available():
+        raise ReferenceUnavailable("reference tree not present at %s" % REF_ROOT)
+    import warnings
+    mods = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name in ("HumanAug", "Evaluation", "HumanPts"):
+            path = os.path.join(REF_ROOT, "pylib", name + ".py")
+            with open(path, "r") as f:
+                src = f.read().expandtabs(8)
+            src = re.sub(r"^(\s*)print\s+'([^']*)'\s*$", r"\1print('\2')", src, flags=re.M)
+            mod = types.ModuleType("reference_pylib_" + name)
+            mod.__file__ = path
+            # stand-ins during the exec only: the implicit relative import of Evaluation.py:4, and matplotlib.path
+            # (HumanPts.py:6, used by a polygon helper that is not on the path) which this image does not have
+            stubs = {}
+            if name == "Evaluation":
+                stubs["HumanAug"] = mods["HumanAug"]
+            if name == "HumanPts" and "matplotlib" not in sys.modules:
+                mpl, mpath = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.path")
+                mpath.Path = object
+                mpl.path = mpath
+                stubs.update({"matplotlib": mpl, "matplotlib.path": mpath})
+            saved = {k: sys.modules.get(k) for k in stubs}
+            sys.modules.update(stubs)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    exec(compile(src, path, "exec"), mod.__dict__)
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        sys.modules.pop(k, None)
+                    else:
+                        sys.modules[k] = v
+            mods[name] = mod
+    return mods

@@ -166,3 +166,73 @@ def test_product_synthetic_matches_oracle_copy():
     for seed in (0, 7):
         a, b = prod.make_inputs(2, 5, seed=seed), synthetic.make_inputs(2, 5, seed=seed)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ---- validation path + target heat maps: oracle/evaluation_oracle.py against the REAL pylib functions -----------------
+def _pylib_fixture(golden_dir):
+    from oracle import gen_golden
+    fx = torch.load(os.path.join(golden_dir, "pylib_eval.pt"), weights_only=False)
+    inp = gen_golden.pylib_inputs()
+    fp = torch.stack([inp["output"].double().sum(), inp["target"].double().sum(), inp["pts"].double().sum()])
+    assert torch.allclose(fp, fx["inputs_fingerprint"], rtol=0, atol=1e-9), "seeded inputs drifted from the fixture's"
+    return fx, inp
+
+
+def test_evaluation_oracle_matches_reference_fixture(golden_dir):
+    """get_preds / accuracy / final_preds / accuracy_origin_res / calc_dists of pylib/Evaluation.py, flip helpers of
+    pylib/HumanAug.py and pts2heatmap of pylib/HumanPts.py: outputs recorded from the real reference functions."""
+    import numpy as np
+    fx, inp = _pylib_fixture(golden_dir)
+    out, tgt, res = inp["output"], inp["target"], [64, 64]
+    assert torch.equal(evaluation_oracle.get_preds(out), fx["get_preds"])
+    assert torch.allclose(evaluation_oracle.accuracy(out, tgt, inp["idxs"]), fx["accuracy"], atol=1e-7)
+    fp = evaluation_oracle.final_preds(out.clone(), inp["center"], inp["scale"], res, inp["rot"])
+    assert torch.equal(fp, fx["final_preds"])
+    assert torch.allclose(evaluation_oracle.calc_dists(fp, inp["grnd_pts"], inp["normalizers"], use_zero=True),
+                          fx["calc_dists"], atol=1e-6)
+    assert torch.allclose(evaluation_oracle.accuracy_origin_res(out.clone(), inp["center"], inp["scale"], res,
+                                                                inp["grnd_pts"], inp["normalizers"], inp["rot"]),
+                          fx["accuracy_origin_res"], atol=1e-7)
+    small = out[:2, :, 20:28, 20:28].contiguous()
+    assert torch.equal(evaluation_oracle.flip_channels(small.clone()), fx["flip_channels"])
+    assert torch.equal(evaluation_oracle.shuffle_channels_for_horizontal_flipping(small.clone(), inp["flip_index"]),
+                       fx["shuffle"])
+    h, v = evaluation_oracle.pts2heatmap(inp["pts"][0].numpy().astype(np.float64), (64, 64), 1)
+    assert np.abs(h - fx["pts2heatmap"].numpy()).max() < 1e-6 and np.abs(v - fx["valid_pts"].numpy()).max() == 0
+
+
+def test_product_validation_dropins_match_reference_fixture(golden_dir):
+    """The vectorised drop-ins of cunet_b200.pylib (device-agnostic arithmetic) against the same recorded outputs."""
+    from cunet_b200.pylib import Evaluation, HumanAug, HumanPts
+    fx, inp = _pylib_fixture(golden_dir)
+    out, tgt, res = inp["output"], inp["target"], [64, 64]
+    preds, gts = fx["get_preds"], evaluation_oracle.get_preds(tgt)
+    assert torch.allclose(Evaluation.accuracy_from_preds(preds, gts, 64, inp["idxs"]), fx["accuracy"], atol=1e-6)
+    got = Evaluation.final_preds_from_coords(out, preds, inp["center"], inp["scale"], res, inp["rot"])
+    assert (got - fx["final_preds"]).abs().max() <= 1.0 and ((got - fx["final_preds"]).abs() > 0).float().mean() < 0.03
+    assert torch.allclose(Evaluation.calc_dists(fx["final_preds"], inp["grnd_pts"], inp["normalizers"], use_zero=True),
+                          fx["calc_dists"], atol=1e-5)
+    small = out[:2, :, 20:28, 20:28].contiguous()
+    assert torch.equal(HumanAug.flip_channels(small), fx["flip_channels"])
+    assert torch.equal(HumanAug.shuffle_channels_for_horizontal_flipping(small, inp["flip_index"]), fx["shuffle"])
+    hm, valid = HumanPts.pts2heatmap(inp["pts"][0], (64, 64), 1)
+    assert (hm - fx["pts2heatmap"]).abs().max() < 1e-6 and (valid.double() - fx["valid_pts"]).abs().max() < 1e-6
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_evaluation_oracle_live_against_reference():
+    """Side by side with the real pylib modules executed in the build container (different seed than the fixture)."""
+    import numpy as np
+    from oracle import gen_golden
+    mods = ref_loader.load_reference_pylib()
+    inp = gen_golden.pylib_inputs(seed=23)
+    out, tgt, res = inp["output"], inp["target"], [64, 64]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert torch.equal(evaluation_oracle.get_preds(out), mods["Evaluation"].get_preds(out.clone()))
+        assert torch.allclose(evaluation_oracle.accuracy(out, tgt, inp["idxs"]),
+                              mods["Evaluation"].accuracy(out.clone(), tgt.clone(), inp["idxs"]), atol=1e-7)
+        assert torch.equal(evaluation_oracle.final_preds(out.clone(), inp["center"], inp["scale"], res, inp["rot"]),
+                           mods["Evaluation"].final_preds(out.clone(), inp["center"], inp["scale"], res, inp["rot"]))
+        t_ref = mods["HumanAug"].GetTransform(np.array([320.0, 410.0]), 1.7, 30.0, 64, 200)
+        assert np.abs(evaluation_oracle.get_transform(np.array([320.0, 410.0]), 1.7, 30.0, 64, 200) - t_ref).max() < 1e-12
