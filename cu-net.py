@@ -46,7 +46,8 @@ def parse(argv=None):
     ap.add_argument("--loss_num", type=int, default=16)
     ap.add_argument("--lr", type=float, default=2.5e-4)
     ap.add_argument("--bs", type=int, default=24)
-    ap.add_argument("--adjust_lr", type=str2bool, default=False)
+    ap.add_argument("--adjust_lr", type=str2bool, default=True,
+                    help="the reference's schedule (utils/util.py:106-119, applied every epoch at cu-net.py:119)")
     ap.add_argument("--resume_prefix", type=str, default="")
     ap.add_argument("--nEpochs", type=int, default=200)
     ap.add_argument("--print_freq", type=int, default=10)
@@ -187,6 +188,9 @@ def run(opt, loader=None):
     for epoch in range(history.epoch[-1]["epoch"] + 1, opt.nEpochs):
         if opt.adjust_lr:
             tr.set_lr(adjust_lr(opt, epoch))
+            if opt_torch is not None:
+                for group in opt_torch.param_groups:
+                    group["lr"] = opt.lr
         t0, n_img, last = time.time(), 0, 0.0
         for i, (img, hm) in enumerate(loader_fn(epoch)):
             if opt.fused:

@@ -114,3 +114,30 @@ def test_entry_point_resume(tmp_path):
     assert opt.lr == 5e-4 and hist_b.epoch[-1]["epoch"] == 11 and "param_groups" in state
     for k, v in b.state_dict().items():
         assert torch.equal(v, a.state_dict()[k]), k
+
+
+def test_lr_schedule_matches_reference():
+    """cu-net.py::adjust_lr == utils/util.py:106-119 (x0.2 at epoch 101, x0.5 at 141 and 161), executed side by side."""
+    import importlib.util
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("cu_net_entry", os.path.join(root, "cu-net.py"))
+    entry = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(entry)
+    ours = types.SimpleNamespace(lr=2.5e-4)
+    lrs = [entry.adjust_lr(ours, e) for e in range(200)]
+    assert lrs[100] == 2.5e-4 and abs(lrs[101] - 5e-5) < 1e-18 and abs(lrs[141] - 2.5e-5) < 1e-18 \
+        and abs(lrs[199] - 1.25e-5) < 1e-18
+    if ref_loader.available():
+        import contextlib
+        import io
+        src = open(os.path.join(ref_loader.REF_ROOT, "utils", "util.py")).read()
+        start = src.index("def adjust_lr(opt, optimizer, epoch):")
+        ns = {}
+        exec(src[start:src.index("def AdjustLR")], ns)                 # the function only (the module imports visdom etc.)
+        ref_opt = types.SimpleNamespace(lr=2.5e-4)
+        fake = types.SimpleNamespace(param_groups=[{"lr": 2.5e-4}])
+        with contextlib.redirect_stdout(io.StringIO()):
+            for e in range(200):
+                ns["adjust_lr"](ref_opt, fake, e)
+                assert abs(ref_opt.lr - lrs[e]) < 1e-18, e
