@@ -141,3 +141,17 @@ def test_lr_schedule_matches_reference():
             for e in range(200):
                 ns["adjust_lr"](ref_opt, fake, e)
                 assert abs(ref_opt.lr - lrs[e]) < 1e-18, e
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_quantizer_target_convs_match_reference_module_order():
+    """QuanOp / BinOp pick nn.Conv2d modules by their modules()-index (utils/quantize.py:80-102): the parameter tree
+    must enumerate its convs in the reference's order (features, hg, linears, intermedia -- models/cu_net.py:299-320)."""
+    import torch.nn as nn
+    ours, ref = _nets(class_num=5, layer_num=3, order=2, loss_num=3)
+    conv_names = lambda net: [n for n, m in net.named_modules() if isinstance(m, nn.Conv2d)]   # noqa: E731
+    a, b = conv_names(ours), conv_names(ref)
+    assert a == b and len(a) > 10
+    assert a[0] == "features.conv0" and a[-1].startswith("intermedia.adapters.")
+    shapes = lambda net: [tuple(m.weight.shape) for m in net.modules() if isinstance(m, nn.Conv2d)]   # noqa: E731
+    assert shapes(ours) == shapes(ref)
