@@ -8,8 +8,8 @@ from tests import plan_emulator
 from cunet_b200 import plan as plan_mod
 
 
-@pytest.mark.parametrize("cfg", [(5, 2, 1, 2), (4, 3, 2, 2), (3, 3, 0, 3), (6, 4, 1, 2)],
-                         ids=["L2K1", "L3K2", "L3K0", "L4K1"])
+@pytest.mark.parametrize("cfg", [(5, 2, 1, 2), (4, 3, 2, 2), (3, 3, 0, 3), (6, 4, 1, 2), (3, 4, 3, 4)],
+                         ids=["L2K1", "L3K2", "L3K0", "L4K1", "L4K3"])
 def test_plan_matches_oracle(cfg):
     class_num, L, K, loss_num = cfg
     plan = plan_mod.Plan(class_num, L, K, loss_num, in_res=64)
