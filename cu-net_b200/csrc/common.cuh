@@ -83,6 +83,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Optional in-kernel timeline (only in builds with -DCUNET_TRACE, see tools/build_trace.sh; the default build compiles
+// these to nothing): CTA 0 stores clock64() at role milestones into a device buffer handed over by a per-kernel
+// cunet_debug_trace_*(buf) setter; tools/trace_kernels.py prints the timelines.
+#ifdef CUNET_TRACE
+#define CUNET_TRACE_DECL(sym) __device__ long long* sym = nullptr;
+#define CUNET_TRACE_LOAD(var, sym) long long* var = sym;
+#define CUNET_TRACE_MARK(var, slot)                                          \
+  do {                                                                       \
+    if ((var) != nullptr && blockIdx.x == 0) (var)[(slot)] = clock64();      \
+  } while (0)
+#define CUNET_TRACE_SETTER(fn, sym)                                          \
+  extern "C" int fn(void* buf) {                                             \
+    long long* b = reinterpret_cast<long long*>(buf);                        \
+    return cudaMemcpyToSymbol(sym, &b, sizeof(b)) == cudaSuccess ? 0 : -1;   \
+  }
+#else
+#define CUNET_TRACE_DECL(sym)
+#define CUNET_TRACE_LOAD(var, sym)
+#define CUNET_TRACE_MARK(var, slot) \
+  do {                              \
+  } while (0)
+#define CUNET_TRACE_SETTER(fn, sym)
+#endif
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -76,6 +76,10 @@ __device__ __forceinline__ uint4 b3_lds128(uint32_t saddr) {
   return v;
 }
 
+// timeline slots (CUNET_TRACE builds): stage i < 16 -> producer 0+2i, transformer 32+4i, MMA 96+3i, epilogue 144+2i,
+// store issuer 176+2i; 208: dW staging starts, 209: kernel end of the epilogue warps
+CUNET_TRACE_DECL(g_b3_trace)
+
 __device__ __forceinline__ void b3_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid_constant__ cunet_conv_dgrad_params p,
@@ -91,6 +95,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
   const int st1 = min(total, st0 + per);
   const int ns = max(0, st1 - st0);
   const int halo = W + 1;
+  CUNET_TRACE_LOAD(trace, g_b3_trace)
 
   if (tid == 0) {
     mbar_init(&tail->w_full, 1);
@@ -163,10 +168,12 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
         const int lo = max(0, m0 - halo), hi = min(M, m0 + nv + halo);
         const uint32_t gb = (uint32_t)((hi - lo) * 64);
         mbar_wait(&tail->gt_free[b], fpar);
+        if (i < 16) CUNET_TRACE_MARK(trace, 0 + 2 * i);
         mbar_arrive_expect_tx(&tail->gt_full[b], 2u * gb);
         bulk_g2s(smem + B3_G_OFF + b * 2 * B3_GT_BYTES, gsrc + (long)lo * 64, gb, &tail->gt_full[b]);
         bulk_g2s(smem + B3_G_OFF + b * 2 * B3_GT_BYTES + B3_GT_BYTES, tsrc + (long)lo * 64, gb, &tail->gt_full[b]);
         mbar_wait(&tail->x_free[b], fpar);
+        if (i < 16) CUNET_TRACE_MARK(trace, 1 + 2 * i);
         mbar_arrive_expect_tx(&tail->x_full[b], (uint32_t)(nv * 256));
         bulk_g2s(smem + B3_X_OFF + b * 16384, xsrc + (long)m0 * 256, (uint32_t)(nv * 256), &tail->x_full[b]);
       }
@@ -179,11 +186,13 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
         const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
         const uint32_t b = (uint32_t)i & 1u;
         mbar_wait(&tail->g_ready[b], ((uint32_t)i >> 1) & 1u);
+        if (i < 16) CUNET_TRACE_MARK(trace, 176 + 2 * i);
         const uint8_t* src = smem + B3_X_OFF + b * 16384;
         if (p.gacc[0].accumulate) b3_bulk_red_add_bf16(G + (long)m0 * 256, src, (uint32_t)(nv * 256));
         else b3_bulk_s2g(G + (long)m0 * 256, src, (uint32_t)(nv * 256));
         b3_bulk_commit();
         b3_bulk_wait_read0();
+        if (i < 16) CUNET_TRACE_MARK(trace, 177 + 2 * i);
         mbar_arrive(&tail->x_free[b]);
       }
     }
@@ -198,7 +207,9 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       for (int i = 0; i < ns; ++i) {
         const uint32_t b = (uint32_t)i & 1u;
         mbar_wait(&tail->ops_ready, (uint32_t)i & 1u);
+        if (i < 16) CUNET_TRACE_MARK(trace, 96 + 3 * i);
         mbar_wait(&tail->d1_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        if (i < 16) CUNET_TRACE_MARK(trace, 97 + 3 * i);
         tc_fence_after();
         const uint32_t d1 = tmem + B3_D1_COL + b * 64u;
 #pragma unroll
@@ -219,6 +230,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
           umma<bf16>(tmem + 192, ad, make_sdesc_mn<bf16>(bB + 3 * B3_SUB + kk * 2048, B3_SUB), idesc_w2, acc);
         }
         tc_commit(&tail->ops_free);
+        if (i < 16) CUNET_TRACE_MARK(trace, 98 + 3 * i);
       }
       tc_commit(&tail->done);
     }
@@ -230,9 +242,12 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       const int lo = max(0, m0 - halo);
       const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
       const uint32_t gl = smem_u32(smem + B3_G_OFF + b * 2 * B3_GT_BYTES) + (uint32_t)c4 * 16u, tl = gl + B3_GT_BYTES;
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 32 + 4 * i);
       mbar_wait(&tail->gt_full[b], upar);
       mbar_wait(&tail->x_full[b], upar);
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 33 + 4 * i);
       mbar_wait(&tail->ops_free, ((uint32_t)i & 1u) ^ 1u);  // MMAs of the previous stage no longer read the operands
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 34 + 4 * i);
       {
         const int r = rI;
         const int m = m0 + r;
@@ -267,6 +282,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       }
       fence_proxy_async();
       __syncwarp();
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 35 + 4 * i);
       if (lane == 0) {
         mbar_arrive(&tail->ops_ready);
         mbar_arrive(&tail->gt_free[b]);
@@ -281,6 +297,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       const uint32_t b = (uint32_t)i & 1u;
       mbar_wait(&tail->d1_full[b], ((uint32_t)i >> 1) & 1u);
       mbar_wait(&tail->x_full[b], ((uint32_t)i >> 1) & 1u);  // completed long ago: acquires the landed x for this thread
+      if (tid == 384 && i < 16) CUNET_TRACE_MARK(trace, 144 + 2 * i);
       tc_fence_after();
       const uint32_t xa = smem_u32(smem + B3_X_OFF + b * 16384) + (uint32_t)k * 2u;
       const uint32_t tb = tmem + B3_D1_COL + b * 64u + ((uint32_t)(qd * 32) << 16);
@@ -311,6 +328,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       fence_proxy_async();  // G written over x -> visible to the bulk store
       tc_fence_before();
       __syncwarp();
+      if (tid == 384 && i < 16) CUNET_TRACE_MARK(trace, 145 + 2 * i);
       if (lane == 0) {
         mbar_arrive(&tail->g_ready[b]);
         mbar_arrive(&tail->d1_free[b]);
@@ -336,6 +354,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       mbar_wait(&tail->done, 0);
       tc_fence_after();
     }
+    if (tid == 384) CUNET_TRACE_MARK(trace, 208);
 #pragma unroll 1
     for (int hh = 0; hh < 2 && ns > 0; ++hh) {
       for (int j = hf; j < 18; j += 2) {
@@ -354,6 +373,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       }
       b3_named_bar(3, 256);
     }
+    if (tid == 384) CUNET_TRACE_MARK(trace, 209);
   }
 
   tc_fence_before();
@@ -363,6 +383,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
 
 }  // namespace cunet
 using namespace cunet;
+
+CUNET_TRACE_SETTER(cunet_debug_trace_bwd3x3, g_b3_trace)
 
 // 1: handled by the fused kernel; 0: not eligible (caller runs the two generic kernels); <0: error
 static int conv_bwd3x3_try(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, cudaStream_t st) {

@@ -60,6 +60,11 @@ struct F3Geom {
   }
 };
 
+// timeline slots (CUNET_TRACE builds), tile i < 16: producer 0+i (landing issued), transformer 16+3i (start, raw landed +
+// operand free, done), MMA 64+2i (operand ready + accumulator free, issued), epilogue 96+3i (accumulator full, TMEM
+// drained, stores + statistics done)
+CUNET_TRACE_DECL(g_f3_trace)
+
 __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid_constant__ cunet_conv_fwd_params p,
                                                                      int ntiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -70,6 +75,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
   g.H = p.H; g.W = p.W; g.lw = 31 - __clz(p.W); g.S = (p.H + 2) * p.W; g.P = p.N * g.S;
   const int W = p.W;
   const int tile0 = (int)blockIdx.x, tstride = (int)gridDim.x;
+  CUNET_TRACE_LOAD(trace, g_f3_trace)
 
   if (tid == 0) {
     mbar_init(&tail->w_full, 1);
@@ -116,6 +122,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
           if (a < b) total += (uint32_t)(b - a) * 256u;
         }
         mbar_wait(&tail->raw_free, (i & 1u) ^ 1u);
+        if (i < 16) CUNET_TRACE_MARK(trace, 0 + i);
         if (total) mbar_arrive_expect_tx(&tail->raw_full, total);
         else mbar_arrive(&tail->raw_full);
         for (int img = i0; img <= i1; ++img) {
@@ -137,6 +144,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
         const uint32_t b = i & 1u;
         mbar_wait(&tail->a_ready, i & 1u);
         mbar_wait(&tail->acc_free[b], ((i >> 1) & 1u) ^ 1u);
+        if (i < 16) CUNET_TRACE_MARK(trace, 64 + 2 * i);
         tc_fence_after();
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
@@ -151,6 +159,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
         }
         tc_commit(&tail->a_free);
         tc_commit(&tail->acc_full[b]);
+        if (i < 16) CUNET_TRACE_MARK(trace, 65 + 2 * i);
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -170,8 +179,10 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
         rv[t] = g.real(p0w + t, grow, w) ? 1 : 0;
       }
       f3_named_bar(1, 256);
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 16 + 3 * i);
       mbar_wait(&tail->raw_full, i & 1u);
       mbar_wait(&tail->a_free, (i & 1u) ^ 1u);  // MMAs of the previous tile no longer read the operand
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 17 + 3 * i);
 #pragma unroll 4
       for (int j = 0; j < 16; ++j) {
         const int r = rbase + 16 * j;
@@ -181,6 +192,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
       }
       fence_proxy_async();
       __syncwarp();
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 18 + 3 * i);
       if (lane == 0) {
         mbar_arrive(&tail->a_ready);
         mbar_arrive(&tail->raw_free);
@@ -198,6 +210,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
       int grow = 0, w = 0;
       const bool valid = g.real(tile * 128 + row, grow, w);
       mbar_wait(&tail->acc_full[b], (i >> 1) & 1u);
+      if (tid == 384 && i < 16) CUNET_TRACE_MARK(trace, 96 + 3 * i);
       tc_fence_after();
       const uint32_t tb = tmem + b * 128u + ((uint32_t)(qd * 32) << 16);
       float ym[32], yp[32];
@@ -235,6 +248,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->acc_free[b]);  // TMEM buffer drained by this warp
+      if (tid == 384 && i < 16) CUNET_TRACE_MARK(trace, 97 + 3 * i);
       // round to the storage type, store this pixel's 32 channels (64 contiguous bytes)
       uint32_t pk[16];
 #pragma unroll
@@ -271,6 +285,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
         s1 += (double)o[0];
         s2 += (double)q2[0];
       }
+      if (tid == 384 && i < 16) CUNET_TRACE_MARK(trace, 98 + 3 * i);
     }
     if (p.out_stats != nullptr && tile0 < ntiles) {
       atomicAdd(p.out_stats + lane, s1);
@@ -285,6 +300,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
 
 }  // namespace cunet
 using namespace cunet;
+
+CUNET_TRACE_SETTER(cunet_debug_trace_fwd3x3, g_f3_trace)
 
 // Returns 1 when this kernel handled the call, 0 when the caller must use the generic kernel, <0 on error.
 int cunet_conv_fwd3x3_try(const cunet_conv_fwd_params* p, cudaStream_t st) {

@@ -44,6 +44,11 @@ __device__ __forceinline__ uint4 f2_lds128(uint32_t saddr) {
 // landing jobs of one tile (identical in the producer and the transformers): per segment, one job per 16 KB of rows
 __device__ __forceinline__ int f2_jobs_of_seg(const cunet_seg& sg) { return (!sg.up && sg.C == 128) ? 2 : 1; }
 
+// timeline slots (CUNET_TRACE builds), tile i < 16: producer 0+i (tile's first landing issued), transformer 16+3i (start,
+// operand free, all jobs transformed), MMA 64+2i (operand ready + accumulator free, issued), epilogue 96+2i (accumulator
+// full, tile done)
+CUNET_TRACE_DECL(g_f2_trace)
+
 __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid_constant__ cunet_conv_fwd_params p,
                                                                      int ntiles, int a_off, int raw_off, int tail_off) {
   extern __shared__ uint8_t smem_raw[];
@@ -56,6 +61,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
   const int W = p.W, lw = 31 - __clz(p.W);
   const int tile0 = (int)blockIdx.x, tstride = (int)gridDim.x;
   const uint32_t wblk = (uint32_t)p.CoutPad * 128u;  // bytes of one K block of the weight image
+  CUNET_TRACE_LOAD(trace, g_f2_trace)
 
   if (tid == 0) {
     mbar_init(&tail->w_full, 1);
@@ -103,9 +109,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
       mbar_arrive_expect_tx(&tail->w_full, (uint32_t)nkb * wblk);
       bulk_g2s(smem, p.wpack, (uint32_t)nkb * wblk, &tail->w_full);
       int slot = 0;
-      uint32_t ph = 0;
-      for (int tile = tile0; tile < ntiles; tile += tstride) {
+      uint32_t ph = 0, ti = 0;
+      for (int tile = tile0; tile < ntiles; tile += tstride, ++ti) {
         const int m0 = tile * 128, nv = min(128, M - m0);
+        if (ti < 16) CUNET_TRACE_MARK(trace, 0 + ti);
         for (int s = 0; s < p.in.nseg; ++s) {
           const cunet_seg& sg = p.in.seg[s];
           const int nj = f2_jobs_of_seg(sg);
@@ -149,6 +156,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
         const uint32_t b = i & 1u;
         mbar_wait(&tail->a_ready, i & 1u);
         mbar_wait(&tail->acc_free[b], ((i >> 1) & 1u) ^ 1u);
+        if (i < 16) CUNET_TRACE_MARK(trace, 64 + 2 * i);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
           const int nkk = min(4, (Cin - kb * 64 + 15) >> 4);  // 16-channel steps that hold real channels
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
         }
         tc_commit(&tail->a_free);
         tc_commit(&tail->acc_full[b]);
+        if (i < 16) CUNET_TRACE_MARK(trace, 65 + 2 * i);
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -168,7 +177,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
     uint32_t ph = 0, i = 0;
     for (int tile = tile0; tile < ntiles; tile += tstride, ++i) {
       const int m0 = tile * 128, nv = min(128, M - m0);
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 16 + 3 * i);
       mbar_wait(&tail->a_free, (i & 1u) ^ 1u);  // MMAs of the previous tile no longer read the operand
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 17 + 3 * i);
       for (int s = 0; s < p.in.nseg; ++s) {
         const cunet_seg& sg = p.in.seg[s];
         const int nj = f2_jobs_of_seg(sg);
@@ -205,6 +216,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
       }
       fence_proxy_async();
       __syncwarp();
+      if (t == 0 && i < 16) CUNET_TRACE_MARK(trace, 18 + 3 * i);
       if (lane == 0) mbar_arrive(&tail->a_ready);
     }
   } else if (warp >= 12) {
@@ -221,6 +233,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
       const bool valid = row < nv;
       const long grow = (long)m0 + row;
       mbar_wait(&tail->acc_full[b], (i >> 1) & 1u);
+      if (tid == 384 && i < 16) CUNET_TRACE_MARK(trace, 96 + 2 * i);
       tc_fence_after();
       const uint32_t tb = tmem + b * 128u + ((uint32_t)(qd * 32) << 16);
       if (p.out_fp32) {
@@ -295,6 +308,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
+      if (tid == 384 && i < 16) CUNET_TRACE_MARK(trace, 97 + 2 * i);
       if (lane == 0) mbar_arrive(&tail->acc_free[b]);
     }
     if (do_stats && tile0 < ntiles) {
@@ -314,6 +328,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) conv_fwd_v2_kernel(const __grid
 
 }  // namespace cunet
 using namespace cunet;
+
+CUNET_TRACE_SETTER(cunet_debug_trace_fwd_v2, g_f2_trace)
 
 // Opt-in for now: on the bench shapes it matches the round-1 kernel but does not beat it yet, so
 // cunet_conv_fwd keeps the round-1 kernel unless CUNET_FWD_V2_MIN_TILES >= 0 (or the debug setter) enables this one

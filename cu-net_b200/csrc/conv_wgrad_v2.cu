@@ -49,6 +49,11 @@ __device__ __forceinline__ void w2_low_span(int m0, int nvalid, int H, int W, in
   nlow = W >= 64 ? (nvalid >> 1) : (nvalid >> 2);   // one image row: 2 px per window; whole row pairs: 4 px
 }
 
+// timeline slots (CUNET_TRACE builds), stage i < 16 of CTA 0: producer 0+i (stage's first landing issued), transformer
+// 16+4i (start, dT slots landed + B buffer free, dT operand done, all chunk operands done), MMA 80+2i (B ready, stage
+// issued); 120: epilogue starts, 121: epilogue done
+CUNET_TRACE_DECL(g_w2_trace)
+
 __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __grid_constant__ cunet_conv_wgrad_params p,
                                                                        int npad) {
   extern __shared__ uint8_t smem_raw[];
@@ -65,6 +70,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
   const int dTn = 1 + (p.dy.mode == 1 ? 1 : 0) + (p.dy.pooled ? 1 : 0);
   int need_low = p.dy.pooled;
   for (int s = 0; s < p.in.nseg; ++s) need_low |= p.in.seg[s].up;
+  CUNET_TRACE_LOAD(trace, g_w2_trace)
 
   if (tid == 0) {
     for (int s = 0; s < W2_NSLOT; ++s) {
@@ -113,6 +119,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
         if (need_low) w2_low_span(m0, nv, p.H, p.W, low0, nlow);
         const int r0 = p.dy.pooled ? low0 : m0, nr = p.dy.pooled ? nlow : nv;
         land(reinterpret_cast<const char*>(p.dy.g) + (long)r0 * ldo, (uint32_t)(nr * ldo));
+        if (st - st0 < 16) CUNET_TRACE_MARK(trace, 0 + (st - st0));
         if (p.dy.mode == 1) land(reinterpret_cast<const char*>(p.dy.t) + (long)r0 * ldo, (uint32_t)(nr * ldo));
         if (p.dy.pooled) land(p.dy.pool_idx + (long)r0 * p.dy.C, (uint32_t)(nr * p.dy.C));
         for (int s = 0; s < p.in.nseg; ++s) {
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
       for (int st = st0; st < st1; ++st, ++si) {
         const uint32_t bb = si & 1;
         mbar_wait(&tail->b_full[bb], (si >> 1) & 1);
+        if (si < 16) CUNET_TRACE_MARK(trace, 80 + 2 * si);
         const uint32_t b = smem_u32(smem + W2_B_OFF + bb * 16384);
         for (int c = 0; c < nchunk; ++c, ++ai) {
           const uint32_t ab = ai % 3;
@@ -143,6 +151,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
           tc_commit(&tail->a_free[ab]);
         }
         tc_commit(&tail->b_free[bb]);
+        if (si < 16) CUNET_TRACE_MARK(trace, 81 + 2 * si);
       }
       tc_commit(&tail->done);
     }
@@ -200,10 +209,12 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
       const int* rpos = tail->row_pos[par];
       // ---- gradient operand dT -> B[par]
       const uint32_t jg = jn, jt = jn + 1, jx = jn + (p.dy.mode == 1 ? 2 : 1);
+      if (t == 0 && si < 16) CUNET_TRACE_MARK(trace, 16 + 4 * si);
       mbar_wait(&tail->slot_full[jg & 7], (jg >> 3) & 1);
       if (p.dy.mode == 1) mbar_wait(&tail->slot_full[jt & 7], (jt >> 3) & 1);
       if (p.dy.pooled) mbar_wait(&tail->slot_full[jx & 7], (jx >> 3) & 1);
       mbar_wait(&tail->b_free[par], ((si >> 1) & 1) ^ 1);
+      if (t == 0 && si < 16) CUNET_TRACE_MARK(trace, 17 + 4 * si);
       {
         const uint8_t* rg = smem + (jg & 7) * W2_SLOT;
         const uint8_t* rt = smem + (jt & 7) * W2_SLOT;
@@ -239,6 +250,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
         if (p.dy.mode == 1) mbar_arrive(&tail->slot_empty[jt & 7]);
         if (p.dy.pooled) mbar_arrive(&tail->slot_empty[jx & 7]);
       }
+      if (t == 0 && si < 16) CUNET_TRACE_MARK(trace, 18 + 4 * si);
       jn += dTn;
       // ---- activation operand per chunk -> A ring
 #pragma unroll
@@ -271,10 +283,12 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
         ++ai;
       }
       jn += p.in.nseg;
+      if (t == 0 && si < 16) CUNET_TRACE_MARK(trace, 19 + 4 * si);
     }
     // ============================================================== epilogue: TMEM -> red.global.add
     if (st1 > st0) {
       mbar_wait(&tail->done, 0);
+      if (t == 0) CUNET_TRACE_MARK(trace, 120);
       tc_fence_after();
       const int e = warp - 2;
       const int qd = warp & 3, hf = e >> 2;
@@ -295,6 +309,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
           }
         }
       }
+      if (t == 0) CUNET_TRACE_MARK(trace, 121);
     }
   }
   tc_fence_before();
@@ -304,6 +319,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_v2_kernel(const __gr
 
 }  // namespace cunet
 using namespace cunet;
+
+CUNET_TRACE_SETTER(cunet_debug_trace_wgrad_v2, g_w2_trace)
 
 // Returns 1 when the v2 kernel handled the call, 0 when the caller must use the generic kernel, <0 on error.
 int cunet_conv_wgrad_v2_try(const cunet_conv_wgrad_params* p, cudaStream_t st) {

@@ -6,7 +6,8 @@ from tests import ops_ref
 lib.load()
 dtype = lib.BF16
 dev = torch.device("cuda")
-def bench(n,h,w,seg_c,ups,cout,taps,pool=False):
+def make(n,h,w,seg_c,ups,cout,taps,pool=False):
+    """Forward-op parameter struct on random data (returns the struct and the tensors that must stay alive)."""
     g = torch.Generator().manual_seed(0)
     srcs,stats,counts=[],[],[]
     for c,up in zip(seg_c,ups):
@@ -25,6 +26,11 @@ def bench(n,h,w,seg_c,ups,cout,taps,pool=False):
     p=lib.ConvFwdParams(); fill_concat(p.inp,srcs,stats,counts,ups,gamma,beta,gamma,gamma,True)
     p.N,p.H,p.W,p.taps=n,h,w,taps; p.wpack,p.Cout,p.CoutPad=wpack.data_ptr(),cout,cout
     p.out,p.out_ld,p.out_fp32=out.data_ptr(),cout,0; p.out_stats=ost.data_ptr(); p.pool=int(pool); p.pool_idx=pidx.data_ptr(); p.dtype=dtype
+    return p, (srcs, stats, gamma, beta, weight, wpack, dd, out, ost, pidx)
+
+def bench(n,h,w,seg_c,ups,cout,taps,pool=False):
+    p, keep = make(n,h,w,seg_c,ups,cout,taps,pool)
+    cin=sum(seg_c)
     for _ in range(5): lib.conv_fwd(p)
     # eager back-to-back
     e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
