@@ -12,8 +12,18 @@ Call protocol (identical to cu-net-prev-version-wig.py:165,189-190 / cu-net-prev
 
 Differences from the reference, on purpose: the bit widths are constructor arguments (defaults = the reference's
 flag defaults bits_w=1, bits_i=8, bits_g=8, options/train_options.py:33-38) instead of an argparse run at import
-time (utils/quantize.py:8-11).  Target selection is the reference's: nn.Conv2d modules with modules()-index
-1 .. count-2 (utils/quantize.py:80-102).
+time (utils/quantize.py:8-11).
+
+Target selection is the reference's rule -- nn.Conv2d modules with modules()-index 1 .. count-2
+(utils/quantize.py:80-102, models/cu_net_prev_version.py:19-41) -- applied to the module tree the reference applies it
+to.  Both quantizers are only ever built on the *prev-version* models (cu-net-prev-version-bin.py:50,65,
+cu-net-prev-version-wig.py:50,65), where the bottleneck 1x1 and every adapter are ``_EfficientDensenetBottleneck``
+modules holding bare Parameters (cu_net_prev_version.py:118-157,166,217-231,294), so the nn.Conv2d set there is conv0
+(:451), the dense-layer 3x3 ``conv.2`` (:170) and the ``layer_num`` heads (:348,463-466): for CU-Net-8 the rule selects
+72 x [32,128,3,3] + 7 x [C,128,1,1].  The drop-in tree of models/cu_net.py registers every 1x1 as nn.Conv2d, so the
+bare rule would select ~262 tensors there and train a different network; ``targets="prev_version"`` (the default for
+a CU-Net drop-in module) reproduces the reference's set, ``targets="all_conv2d"`` is the bare rule (the default for any
+other nn.Module).  tests/golden/binop_targets.pt pins the set against the REAL BinOp constructor.
 """
 import ctypes as C
 
@@ -23,15 +33,38 @@ import torch.nn as nn
 from .. import lib as L
 
 
-def _targets(model):
-    convs = [m for m in model.modules() if isinstance(m, nn.Conv2d)]
-    return convs[1:len(convs) - 1]          # leave out the first and the last Conv2d
+def prev_version_conv_names(model):
+    """Names of the drop-in tree's convs that are nn.Conv2d in the prev-version models, in modules() order."""
+    names = []
+    for name, m in model.named_modules():
+        if isinstance(m, nn.Conv2d) and (name == "features.conv0" or name.endswith(".conv2")
+                                         or (name.startswith("linears.") and name.endswith(".conv"))):
+            names.append(name)
+    return names
+
+
+def target_names(model, targets="auto"):
+    """Module names of the quantizer's target convs: modules()-index 1 .. count-2 of the selected Conv2d set."""
+    if targets == "auto":
+        targets = "prev_version" if hasattr(model, "plan") and hasattr(model, "loss_anchors") else "all_conv2d"
+    if targets == "prev_version":
+        names = prev_version_conv_names(model)
+    elif targets == "all_conv2d":
+        names = [n for n, m in model.named_modules() if isinstance(m, nn.Conv2d)]
+    else:
+        raise ValueError("targets must be 'auto', 'prev_version' or 'all_conv2d'")
+    return names[1:len(names) - 1]          # leave out the first and the last Conv2d
+
+
+def _targets(model, targets="auto"):
+    mods = dict(model.named_modules())
+    return [mods[n] for n in target_names(model, targets)]
 
 
 class _MultiTensorOp(object):
-    def __init__(self, model):
+    def __init__(self, model, targets="auto"):
         L.load()
-        self.target_modules = [m.weight for m in _targets(model)]
+        self.target_modules = [m.weight for m in _targets(model, targets)]
         self.num_of_params = len(self.target_modules)
         for w in self.target_modules:
             if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
@@ -63,8 +96,8 @@ class _MultiTensorOp(object):
 class QuanOp(_MultiTensorOp):
     """utils/quantize.py:77-175."""
 
-    def __init__(self, model, bits_w=1, bits_g=8):
-        super(QuanOp, self).__init__(model)
+    def __init__(self, model, bits_w=1, bits_g=8, targets="auto"):
+        super(QuanOp, self).__init__(model, targets)
         self.bits_w, self.bits_g = int(bits_w), int(bits_g)
 
     def quantization(self):

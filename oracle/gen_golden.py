@@ -117,6 +117,91 @@ def quant_case(name, bits_w, seed):
                 "num_targets": op.num_of_params}, os.path.join(OUT, name))
 
 
+def binop_case(name, seed):
+    """Run the REAL BinOp (models/cu_net_prev_version.py:17-92, loaded by ref_loader.load_reference_binop) on a stack
+    of Conv2d modules shaped like its target set in the prev-version model: conv0, dense-layer 3x3s, heads."""
+    BinOp = ref_loader.load_reference_binop()
+    gen = torch.Generator().manual_seed(seed)
+    shapes = [(8, 3, 7, 7), (32, 128, 3, 3), (6, 128, 3, 3), (16, 128, 1, 1), (68, 128, 1, 1), (16, 128, 1, 1)]
+    convs = []
+    for co, ci, k, _ in shapes:
+        m = nn.Conv2d(ci, co, k, bias=False)
+        m.weight.data = (torch.rand(co, ci, k, k, generator=gen) * 2 - 1) * 1.5     # some |w| > 1: the clamp bites
+        convs.append(m)
+    model = nn.Sequential(*convs)
+    w0 = [m.weight.data.clone() for m in convs]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        op = BinOp(model)
+        op.binarization()
+        wb = [m.weight.data.clone() for m in convs]
+        grads = [torch.randn(m.weight.shape, generator=gen) * 0.01 for m in convs]
+        for m, g in zip(convs, grads):
+            m.weight.grad = g.clone()
+        op.restore()
+        wr = [m.weight.data.clone() for m in convs]
+        op.updateBinaryGradWeight()
+        gb = [m.weight.grad.clone() for m in convs]
+    torch.save({"w0": w0, "wb": wb, "wr": wr, "g0": grads, "gb": gb, "num_targets": op.num_of_params},
+               os.path.join(OUT, name))
+
+
+def binop_targets_case(name):
+    """Which tensors the reference's quantizers touch in the prev-version model (cu-net-prev-version-bin.py:50,65;
+    cu-net-prev-version-wig.py:50,65): nn.Conv2d modules in modules() order with index 1 .. count-2.  The prev-version
+    module cannot be constructed here (removed torch APIs), but its nn.Conv2d set is decided by three constructor
+    sites only -- conv0 (cu_net_prev_version.py:451), one 3x3 ``conv.2`` per _DenseLayer (:170; the bottleneck 1x1 and
+    every adapter are _EfficientDensenetBottleneck modules holding bare Parameters, :118-157, :166, :217-231, :294),
+    one 1x1 ``conv`` per head (:348, ``layer_num`` heads :463-466) -- and by the registration order features, hg
+    (down_blocks, up_blocks, neck_block :394-399), linears, intermedia (:450-470).  This builds a skeleton with exactly
+    those Conv2d leaves in that order and lets the REAL BinOp constructor select from it."""
+    BinOp = ref_loader.load_reference_binop()
+    out = {}
+    for L, class_num in ((2, 16), (8, 16), (8, 68)):
+        root = nn.Module()
+        root.features = nn.Sequential(nn.Conv2d(3, 128, 7, 2, 3, bias=False))
+        hg = nn.Module()
+
+        def block():
+            b = nn.Module()
+            b.layers = nn.ModuleList([nn.Sequential(nn.Conv2d(128, 32, 3, 1, 1, bias=False)) for _ in range(L)])
+            return b
+        hg.down_blocks = nn.ModuleList([block() for _ in range(4)])
+        hg.up_blocks = nn.ModuleList([block() for _ in range(4)])
+        hg.neck_block = block()
+        root.hg = hg
+        root.linears = nn.ModuleList([nn.Sequential(nn.Conv2d(128, class_num, 1, bias=False)) for _ in range(L)])
+        names = {id(m.weight): n for n, m in root.named_modules() if isinstance(m, nn.Conv2d)}
+        op = BinOp(root)
+        out["L%d_C%d" % (L, class_num)] = dict(
+            num_targets=op.num_of_params,
+            shapes=[tuple(w.shape) for w in op.target_modules],
+            names=[names[id(w)] for w in op.target_modules])
+    torch.save(out, os.path.join(OUT, name))
+
+
+def quaninput_case(name, seed):
+    """QuanInput (utils/quantize.py:47-63): its forward / backward bodies are executed as plain functions of the real
+    module (the legacy non-static autograd.Function cannot be *applied* on modern torch, but its two methods are
+    ordinary python) with a stand-in ``self`` that implements save_for_backward / saved_tensors."""
+    out = {}
+    for bits_i in (8, 4):
+        q = ref_loader.load_reference_quantize(1, bits_i=bits_i)
+        gen = torch.Generator().manual_seed(seed + bits_i)
+        x = torch.randn(4, 16, 8, 8, generator=gen) * 0.8
+        x.view(-1)[:6] = torch.tensor([1.0, -1.0, 0.9921875, 0.99609375, 0.00390625, -0.01171875])   # edges / ties
+        gy = torch.randn(x.shape, generator=gen)
+
+        class Ctx(object):
+            def save_for_backward(self, *t):
+                self.saved_tensors = t
+        ctx = Ctx()
+        y = q.QuanInput.forward(ctx, x.clone())
+        gx = q.QuanInput.backward(ctx, gy.clone())
+        out[bits_i] = dict(x=x, y=y, gy=gy, gx=gx)
+    torch.save(out, os.path.join(OUT, name))
+
+
 def pylib_inputs(seed=11):
     """Seeded inputs of the validation-path fixture (shared with tests/test_oracle_golden.py)."""
     n, c = 3, 16
@@ -181,6 +266,9 @@ def main():
     real_case("real_L2_K1_C68_n1.pt", 2, 1, 2, 68, 1, seed=0)
     for bw in (1, 2, 8):
         quant_case("quanop_bits%d.pt" % bw, bw, seed=20 + bw)
+    binop_case("binop.pt", seed=31)
+    binop_targets_case("binop_targets.pt")
+    quaninput_case("quaninput.pt", seed=41)
     print("golden fixtures written to", OUT)
 
 

@@ -96,6 +96,46 @@ def load_reference_quantize(bits_w, bits_i=8, bits_g=8, exp_dir="/tmp/cunet_ref_
                 sys.modules[k] = v
 
 
+def load_reference_binop():
+    """The reference's ``BinOp`` class (models/cu_net_prev_version.py:17-92) as an executable class object.
+
+    The module itself cannot be imported (``torch._thnn`` / ``type2backend`` at :8 are gone), and the class body
+    relies on torch-0.1.12 semantics in two ways.  Both are patched IN MEMORY on the text of lines 17-92 only, with
+    exactly the substitutions the reference's own authors made when they ported the sibling class QuanOp from
+    utils/quantize_prev_version.py (0.1.12) to utils/quantize.py (0.4) -- `diff` of those two files:
+      * reductions kept their dimension: ``.mean(1)`` -> ``.mean(1, True)``, ``.norm(1, 3)`` -> ``.norm(1, 3, True)``,
+        ``.sum(k)`` -> ``.sum(k, True)``                                   (quantize.py:113,130-131,162-163,169-170)
+      * method calls with ``out=``: ``x.clamp(a, b, out=x)`` / ``x.sign().mul(m, out=x)`` -> assignment of the result
+                                                                            (quantize.py:133-134)
+    Nothing is copied into this repository."""
+    if not available():
+        raise ReferenceUnavailable("reference tree not present at %s" % REF_ROOT)
+    path = os.path.join(REF_ROOT, "models", "cu_net_prev_version.py")
+    with open(path, "r") as f:
+        lines = f.read().split("\n")
+    assert lines[16].startswith("class BinOp") and lines[93].startswith("class _SharedAllocation"), \
+        "reference source changed; update the line range"
+    src = "\n".join(lines[16:92])
+    subs = [
+        (".data.mean(1).", ".data.mean(1, True)."),
+        (".norm(1, 3)", ".norm(1, 3, True)"),
+        (".sum(2).sum(1).div(n)", ".sum(2, True).sum(1, True).div(n)"),
+        ("m_add.sum(3)", "m_add.sum(3, True)"),
+        ("self.target_modules[index].data.clamp(-1.0, 1.0,\n                    out = self.target_modules[index].data)",
+         "self.target_modules[index].data = self.target_modules[index].data.clamp(-1.0, 1.0)"),
+        ("self.target_modules[index].data.sign()\\\n                    .mul(m.expand(s), out=self.target_modules[index].data)",
+         "self.target_modules[index].data = self.target_modules[index].data.sign().mul(m.expand(s))"),
+    ]
+    for a, b in subs:
+        assert a in src, "reference BinOp source changed; update the substitution %r" % a
+        src = src.replace(a, b)
+    import numpy
+    import torch
+    ns = {"torch": torch, "nn": torch.nn, "numpy": numpy}
+    exec(compile(src, path + ":17-92", "exec"), ns)
+    return ns["BinOp"]
+
+
 def load_reference_pylib():
     """Namespaces of the reference's pylib/HumanAug.py, pylib/Evaluation.py, pylib/HumanPts.py as module objects."""
     if not available():

@@ -76,6 +76,21 @@ CASES = [
     ("1x1_up_tail", 3, 4, 4, [128, 128, 32], [1, 0, 0], 128, 1, "bn", None),
     ("3x3_tail", 3, 4, 4, [128], [0], 32, 9, "bn", None),
     ("1x1_big_bn", 4, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, "bn", None),
+    # ---- the shapes bench.py runs (BASELINE.json configs[2]: batch 24): 768 tiles of 128 pixels on 148 persistent
+    # CTAs, i.e. ~5 tiles per CTA -- landing-ring wrap across tiles, in-place G over the landed x, double-buffered
+    # TMEM across work items.  Segment i of every case accumulates when i is odd, so both `accumulate` values are
+    # exercised at every shape.
+    ("1x1_320_up_b24", 24, 64, 64, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, "bn", None),   # up_blocks.0 adapter
+    ("1x1_288_up_b24", 24, 64, 64, [128, 128, 32], [1, 0, 0], 128, 1, "bn", None),          # up_blocks.0 conv1
+    ("1x1_192_pool_b24", 24, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, "pool", None),       # down_blocks.0 ahead
+    ("1x1_256_b24", 24, 64, 64, [128, 128], [0, 0], 128, 1, "bn", None),                    # intermedia adapter
+    ("1x1_160_b24", 24, 64, 64, [128, 32], [0, 0], 128, 1, "bn", None),                     # down_blocks.0 conv1
+    ("head68_b24", 24, 64, 64, [128], [0], 68, 1, "plain", 80),                             # heat-map head
+    ("1x1_320_up_32_b24", 24, 32, 32, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, "bn", None),  # 192 tiles x 3 chunks
+    ("1x1_192_pool_32_b24", 24, 32, 32, [128, 32, 32], [0, 0, 0], 128, 1, "pool", None),
+    ("1x1_320_up_16_b24", 24, 16, 16, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, "bn", None),  # 48 x 3: split mode
+    ("1x1_192_pool_8_b24", 24, 8, 8, [128, 32, 32], [0, 0, 0], 128, 1, "pool", None),
+    ("1x1_320_up_b3", 3, 64, 64, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, "bn", None),     # 3 img/GPU (strong scaling)
 ]
 
 

@@ -42,6 +42,61 @@ def test_quanop_matches_reference_fixture(golden_dir, bits_w):
         assert torch.equal(m.weight.grad.cpu(), ref), i
 
 
+def test_binop_matches_reference_fixture(golden_dir):
+    """BinOp kernels against the outputs of the REAL BinOp class (tests/golden/binop.pt)."""
+    from cunet_b200.models.cu_net_prev_version import BinOp
+    fx = torch.load(os.path.join(golden_dir, "binop.pt"), weights_only=False)
+    model = _model(fx["w0"])
+    op = BinOp(model)
+    assert op.num_of_params == fx["num_targets"]
+    op.binarization()
+    convs = [m for m in model.modules() if isinstance(m, nn.Conv2d)]
+    for i, (m, ref) in enumerate(zip(convs, fx["wb"])):
+        got = m.weight.data.cpu()
+        assert (got - ref).abs().max() <= 1e-6 * ref.abs().max(), i
+        assert torch.equal(got.sign(), ref.sign()), i
+    for m, g in zip(convs, fx["g0"]):
+        m.weight.grad = g.clone().cuda()
+    op.restore()
+    for i, (m, ref) in enumerate(zip(convs, fx["wr"])):
+        assert (m.weight.data.cpu() - ref).abs().max() <= 1e-7, i
+    op.updateBinaryGradWeight()
+    for i, (m, ref) in enumerate(zip(convs, fx["gb"])):
+        assert (m.weight.grad.cpu() - ref).abs().max() <= 1e-4 * ref.abs().max(), i
+
+
+def test_quaninput_matches_reference_fixture(golden_dir):
+    """QuanInput kernels against the REAL QuanInput.forward / .backward bodies (tests/golden/quaninput.pt): bit exact."""
+    from cunet_b200.utils.quantize import QuanInput2d
+    fx = torch.load(os.path.join(golden_dir, "quaninput.pt"), weights_only=False)
+    for bits_i, d in fx.items():
+        x = d["x"].cuda().requires_grad_(True)
+        y = QuanInput2d(bits_i)(x)
+        assert torch.equal(y.detach().cpu(), d["y"]), bits_i
+        y.backward(d["gy"].cuda())
+        assert torch.equal(x.grad.cpu(), d["gx"]), bits_i
+
+
+def test_binop_target_set_on_the_dropin_model():
+    """BinOp(net) on the CU-Net drop-in binarises the prev-version set (72 3x3 + 7 heads for L=8), leaves every
+    other conv bit-identical, and restore() brings the mean-centred, clamped full-precision copy back."""
+    from cunet_b200.models.cu_net import create_cu_net
+    from cunet_b200.models.cu_net_prev_version import BinOp
+    torch.manual_seed(0)
+    net = create_cu_net(4, 32, 128, 16, 8, 1, 8, dtype="bf16")
+    net.engine(1, "cuda:0")
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    op = BinOp(net)
+    assert op.num_of_params == 79
+    assert sorted(tuple(w.shape) for w in op.target_modules) == sorted([(32, 128, 3, 3)] * 72 + [(16, 128, 1, 1)] * 7)
+    op.binarization()
+    changed = [n for n, p in net.named_parameters() if not torch.equal(p.detach(), before[n])]
+    assert len(changed) == 79 and all(n.endswith("conv2.weight") or n.startswith("linears.") for n in changed)
+    assert "linears.7.conv.weight" not in changed
+    w = dict(net.named_parameters())["hg.down_blocks.0.layers.0.conv2.weight"].detach()
+    assert (w.abs() - w.abs().mean(dim=(1, 2, 3), keepdim=True)).abs().max() < 1e-6      # sign(w) * mean|w| per filter
+
+
 def test_binop_matches_oracle_on_cunet_shapes():
     from cunet_b200.models.cu_net_prev_version import BinOp
     gen = torch.Generator().manual_seed(5)

@@ -129,6 +129,79 @@ def test_quanop_oracle_matches_reference_fixture(golden_dir, bits_w):
         assert torch.equal(g * 128, torch.round(g * 128)) and g.abs().max() <= 0.9921875
 
 
+def test_binop_oracle_matches_reference_fixture(golden_dir):
+    """oracle/quantize_oracle.binop_* against the outputs of the REAL BinOp (models/cu_net_prev_version.py:17-92,
+    executed by oracle/gen_golden.binop_case through ref_loader.load_reference_binop)."""
+    fx = torch.load(os.path.join(golden_dir, "binop.pt"), weights_only=False)
+    idx = quantize_oracle.target_indices(len(fx["w0"]))
+    assert len(idx) == fx["num_targets"]
+    wb, saved = quantize_oracle.binop_binarization([fx["w0"][i] for i in idx])
+    for j, i in enumerate(idx):
+        assert _close(wb[j], fx["wb"][i], 1e-6), i
+        assert torch.equal(wb[j].sign(), fx["wb"][i].sign()), i
+        assert _close(saved[j], fx["wr"][i], 1e-7), i
+    for i in range(len(fx["w0"])):                 # first / last conv untouched
+        if i not in idx:
+            assert torch.equal(fx["wb"][i], fx["w0"][i]) and torch.equal(fx["gb"][i], fx["g0"][i])
+    gb = quantize_oracle.binop_update_grad([fx["wr"][i] for i in idx], [fx["g0"][i] for i in idx])
+    for j, i in enumerate(idx):
+        assert _close(gb[j], fx["gb"][i], 1e-4), i
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_binop_oracle_live_against_reference():
+    import torch.nn as nn
+    BinOp = ref_loader.load_reference_binop()
+    gen = torch.Generator().manual_seed(77)
+    convs = [nn.Conv2d(ci, co, k, bias=False) for co, ci, k in ((4, 3, 3), (32, 128, 3), (16, 128, 1), (4, 4, 1))]
+    for m in convs:
+        m.weight.data = (torch.rand(m.weight.shape, generator=gen) * 2 - 1) * 1.2
+    w0 = [m.weight.data.clone() for m in convs]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        op = BinOp(nn.Sequential(*convs))
+        op.binarization()
+        wb, saved = quantize_oracle.binop_binarization(w0[1:3])
+        for a, m in zip(wb, convs[1:3]):
+            assert _close(a, m.weight.data, 1e-6)
+        g0 = [torch.randn(m.weight.shape, generator=gen) for m in convs]
+        for m, g in zip(convs, g0):
+            m.weight.grad = g.clone()
+        op.restore()
+        op.updateBinaryGradWeight()
+    for a, m in zip(quantize_oracle.binop_update_grad(saved, g0[1:3]), convs[1:3]):
+        assert _close(a, m.weight.grad, 1e-4)
+
+
+@pytest.mark.parametrize("cfg", [(2, 16), (8, 16), (8, 68)])
+def test_quantizer_target_set_is_the_prev_version_set(golden_dir, cfg):
+    """BASELINE.json configs[3]: the tensors BinOp / QuanOp select on the drop-in module are the ones the REAL BinOp
+    constructor selects on the prev-version model's nn.Conv2d skeleton (tests/golden/binop_targets.pt): for L=8 the
+    72 dense-layer 3x3 convs + 7 of the 8 heads, not the 262 convs of the drop-in tree."""
+    from cunet_b200.models.cu_net import create_cu_net
+    from cunet_b200.utils.quantize import target_names
+    L, C = cfg
+    fx = torch.load(os.path.join(golden_dir, "binop_targets.pt"), weights_only=False)["L%d_C%d" % (L, C)]
+    net = create_cu_net(4, 32, 128, C, L, 1, L)
+    names = target_names(net)                                  # default for a CU-Net drop-in: prev_version
+    mods = dict(net.named_modules())
+    assert len(names) == fx["num_targets"] == 9 * L + L - 1
+    assert [tuple(mods[n].weight.shape) for n in names] == fx["shapes"]
+    skeleton = [n[:-len("conv2")] + "0" if n.endswith("conv2") else n[:-len("conv")] + "0" for n in names]
+    assert skeleton == fx["names"]
+    assert len(target_names(net, "all_conv2d")) == 33 * L - 2
+
+
+def test_quaninput_oracle_matches_reference_fixture(golden_dir):
+    """quantize_oracle.quan_input_* against the REAL QuanInput.forward / .backward bodies (utils/quantize.py:47-63)."""
+    fx = torch.load(os.path.join(golden_dir, "quaninput.pt"), weights_only=False)
+    for bits_i, d in fx.items():
+        assert torch.equal(quantize_oracle.quan_input_forward(d["x"], bits_i), d["y"])
+        assert torch.equal(quantize_oracle.quan_input_backward(d["x"], d["gy"]), d["gx"])
+        sc = 2.0 ** (bits_i - 1)
+        assert torch.equal(d["y"] * sc, torch.round(d["y"] * sc)) and d["y"].abs().max() <= 1 - 1 / sc
+
+
 def test_binop_properties():
     gen = torch.Generator().manual_seed(3)
     w = [(torch.rand(32, 128, 3, 3, generator=gen) * 2 - 1) * 1.3]
