@@ -129,6 +129,34 @@ def cpu_reference(cfg, sample_batch, iters, warmup=1):
     return sample_batch / times[len(times) // 2], best_t
 
 
+def _dump_state(state):
+    """Initial weights -> a temp file for the oracle child process (the checker runs outside this process so that its
+    CPU thread settings and memory stay out of the measured one)."""
+    import tempfile
+    import torch
+    fd, path = tempfile.mkstemp(suffix=".pt", prefix="cunet_state0_")
+    os.close(fd)
+    torch.save(state, path)
+    return path
+
+
+def oracle_loss_main(cfg, batch):
+    """Child mode: multi-loss MSE of the CPU oracle (train-mode BN, forward only) on the bench's rank-0 batch with the
+    weights the B200 arm started from.  Test infrastructure used as the checker only."""
+    import torch
+    from oracle import cunet_oracle, synthetic
+    path = os.environ["CUNET_STATE0"]
+    state = torch.load(path, weights_only=False)
+    os.unlink(path)
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    net = cunet_oracle.OracleCUNet(state, cfg["class_num"], cfg["layer_num"], cfg["order"], cfg["loss_num"])
+    img, hm = synthetic.make_inputs(batch, cfg["class_num"], seed=0)
+    with torch.no_grad():
+        loss = cunet_oracle.multi_loss_mse(net(img), hm)
+    print(json.dumps(dict(loss_oracle=float(loss))))
+    return 0
+
+
 def op_bytes(eng, op, kind):
     """Algorithmic HBM bytes of one launch (DESIGN.md 'Kernels'): every operand read once, every result written once."""
     esz = 2 if eng.tdtype.itemsize == 2 else 4
@@ -164,8 +192,10 @@ def main():
                     help="weak: the config's batch per GPU (default); strong: the config's batch is the GLOBAL batch, "
                          "split over the GPUs like the reference's DataParallel does with --bs (cu-net.py:59,84)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="images in the CPU-baseline sample step")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="images in the CPU-baseline sample step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-loss-check", action="store_true", help="skip the CPU-oracle loss of the first step")
+    ap.add_argument("--oracle-loss", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -185,6 +215,9 @@ def main():
         cfg["layer_num"], cfg["order"], cfg["loss_num"], cfg["class_num"], cfg["batch"], cfg["dtype"],
         ", binary weights (BinOp protocol)" if cfg.get("quant") == "bin" else "")
 
+    if args.oracle_loss:
+        return oracle_loss_main(cfg, cfg["batch"])
+
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
@@ -193,10 +226,14 @@ def main():
             print(json.dumps(dict(impl="reference", unavailable="the CPU reference arm times the full-precision step only")))
             return 0
         ips, cores = cpu_reference(cfg, args.cpu_sample, max(1, min(args.steps, 3)))
+        ref_workload = ("CU-Net-%d order %d loss %d, %d classes, 256x256 -> 64x64 heatmaps, train step on the host CPU: "
+                        "%d-image sample batch, fp32 (torch CPU), %d threads -- bounded sample of the B200 arm's workload "
+                        "(batch %d per GPU, %s)" % (cfg["layer_num"], cfg["order"], cfg["loss_num"], cfg["class_num"],
+                                                    args.cpu_sample, cores, cfg["batch"], cfg["dtype"]))
         line = dict(impl="reference", metric="images_per_sec", value=ips, unit="images/s", n_gpus=args.gpus,
                     steps=args.steps, warmup=args.warmup, ms_per_step=1000.0 * args.cpu_sample / ips,
                     higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=workload),
+                    config=dict(workload=ref_workload, sample_batch=args.cpu_sample, b200_arm_workload=workload),
                     cpu_baseline=dict(value=ips, unit="images/s", cores=cores, kind="port",
                                       sample="%d-image training step (fwd+MSE+bwd+RMSprop) of the same model, median of %d"
                                              % (args.cpu_sample, max(1, min(args.steps, 3)))),
@@ -238,6 +275,9 @@ def main():
     img_h, hm_h = img.pin_memory(), hm.pin_memory()
     tr.load_batch(img_h, hm_h)
     torch.cuda.synchronize()
+    # correctness guard (outside every timed region): the loss of the very first step, from the initial weights, is
+    # reported next to the CPU oracle's loss on the same images and weights -- a wrong step can not score silently
+    state0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()} if rank == 0 else None
 
     def barrier():
         if world > 1:
@@ -262,7 +302,8 @@ def main():
         return ms
 
     # resident-input steps
-    for _ in range(args.warmup):
+    loss_first = float(tr.train_step())
+    for _ in range(args.warmup - 1):
         tr.train_step()
     sampler = ClockSampler(local)
     sampler.start()
@@ -275,15 +316,70 @@ def main():
     loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
 
     def e2e_step():
-        loss = tr.train_step(img_h, hm_h)
+        # every step's inputs cross PCIe from pinned host memory: the copy of the NEXT step's batch is issued on the
+        # copy stream right after this step's launch (Trainer.prefetch), so it overlaps the step's kernels; the
+        # blocking loss read-back ends the step
+        loss = tr.train_step()                     # consumes the batch staged by the previous prefetch
+        tr.prefetch(img_h, hm_h)
         loss_host.copy_(loss.view(1), non_blocking=False)
+    tr.prefetch(img_h, hm_h)
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     e2e = world * B / (ms_e2e / 1000.0)
+    tr._staged = None
+
+    # ---- the reference's multi-GPU semantics (cu-net.py:59,84: --bs is the GLOBAL batch, scattered over the GPUs):
+    # same model, same timing loop, the config's batch split over the ranks.  At N=1 it is the weak-scaling number.
+    strong = None
+    if args.scaling == "weak":
+        gb = CONFIGS[args.config]["batch"] if not args.batch else args.batch
+        if world == 1:
+            strong = dict(global_batch=gb, per_gpu_batch=gb, value=value, unit="images/s", ms_per_step=ms_per_step)
+        elif gb % world == 0:
+            Bs = gb // world
+            tr_s = Trainer(net, Bs, lr=2.5e-4, device=dev, process_group=pg, world_size=world,
+                           use_graph=not args.no_graph, quant=quant)
+            imgs, hms = synthetic.make_inputs(Bs, cfg["class_num"], seed=100 + rank)
+            tr_s.load_batch(imgs.to(dev), hms.to(dev))
+            for _ in range(args.warmup):
+                tr_s.train_step()
+            ms_s = timed(lambda: tr_s.train_step(), args.steps) / args.steps
+            strong = dict(global_batch=gb, per_gpu_batch=Bs, value=gb / (ms_s / 1000.0), unit="images/s", ms_per_step=ms_s,
+                          launches_per_step=tr_s.eng.launches_per_train_step(),
+                          limit="launch-latency floor of the ~%d dependent launches per step (the kernels on <= 16x16 maps "
+                                "are latency-bound whatever the batch), then the exposed ncclAllReduce of the %.1f MB fp32 "
+                                "gradient bucket" % (tr_s.eng.launches_per_train_step(), 4e-6 * tr_s.eng.n_params))
+            del tr_s
 
     if rank != 0:
         return 0
+
+    # ---- the drop-in module API, timed literally as cu-net.py:171-183 drives it (N=1): net(img) -> multi-loss MSE in
+    # torch -> loss.backward() -> torch.optim.RMSprop.step(), host buffers, H2D inside the timed region
+    module_api = None
+    if world == 1 and not cfg.get("quant"):
+        opt_t = torch.optim.RMSprop(net.parameters(), lr=2.5e-4, alpha=0.99, eps=1e-8, momentum=0, weight_decay=0)
+        net.train()
+
+        def module_step():
+            x, t = img_h.to(dev, non_blocking=True), hm_h.to(dev, non_blocking=True)
+            out = net(x)
+            loss = 0
+            for o in out:
+                d = (o - t) ** 2
+                loss = loss + d.sum() / d.numel()
+            opt_t.zero_grad()
+            loss.backward()
+            opt_t.step()
+            loss_host.copy_(loss.detach().double().view(1), non_blocking=False)
+        for _ in range(2):
+            module_step()
+        nst = max(2, args.steps // 2)
+        ms_m = timed(module_step, nst) / nst
+        module_api = dict(value=B / (ms_m / 1000.0), unit="images/s", ms_per_step=ms_m,
+                          path="net(img); loss.backward(); torch.optim.RMSprop.step() (cu-net.py:171-183), eager launches")
+        net.bind_grads()
 
     # ---- roofline of the dominant kernel, measured live (eager launches bracketed by CUDA events)
     eng = tr.eng
@@ -300,7 +396,7 @@ def main():
     acc = {k: [] for k in kinds}
     for _ in range(5):
         tr._fwd_bwd()
-        eng.optimizer_step()
+        tr._opt()
         torch.cuda.synchronize()
         for k in kinds:
             acc[k].append(evs[k][0].elapsed_time(evs[k][1]))
@@ -321,7 +417,24 @@ def main():
     if os.path.exists(tpath) and cfg["dtype"] == "bf16":
         tj = json.load(open(tpath)).get("conv_dgrad")
         if tj:
-            traffic, traffic_src = tj["bytes"], tj["source"]
+            # the capture is only quoted while the kernel source it was taken from is unchanged (sha1 of the .cu file)
+            import hashlib
+            src_file = os.path.join(ROOT, "cu-net_b200", "csrc", tj.get("kernel_file", "conv_dgrad_v2.cu"))
+            sha = hashlib.sha1(open(src_file, "rb").read()).hexdigest() if os.path.exists(src_file) else None
+            if tj.get("kernel_sha1") in (None, sha):
+                traffic, traffic_src = tj["bytes"], tj["source"]
+            else:
+                traffic_src = "stale: %s changed since %s was captured" % (tj.get("kernel_file"), tj["source"])
+    loss_oracle = None
+    if not args.no_loss_check and not cfg.get("quant"):
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--oracle-loss", "--config", args.config,
+                                  "--batch", str(B)] + (["--dtype", args.dtype] if args.dtype else []),
+                                 input=None, capture_output=True, text=True, timeout=600,
+                                 env=dict(os.environ, CUNET_STATE0=_dump_state(state0))).stdout
+            loss_oracle = json.loads(out.strip().splitlines()[-1])["loss_oracle"]
+        except Exception as exc:  # noqa: BLE001
+            loss_oracle = "unavailable: %s" % type(exc).__name__
     train_gflop_img = (3.0 * plan.conv_flops_per_image() - 2.0 * 147 * 128 * 128 * 128) / 1e9
     tflops = value * train_gflop_img / 1e3
     line = dict(
@@ -335,8 +448,13 @@ def main():
                     pdl="programmatic dependent launch between the conv kernels: %s"
                         % ("off" if os.environ.get("CUNET_PDL", "1") == "0" else "on")),
         e2e=dict(value=e2e, unit="images/s", ms_per_step=ms_e2e,
-                 h2d_bytes_per_step=int(img_h.numel() * 4 + hm_h.numel() * 4), d2h_bytes_per_step=8),
+                 h2d_bytes_per_step=int(img_h.numel() * 4 + hm_h.numel() * 4), d2h_bytes_per_step=8,
+                 path="Trainer.train_step() + Trainer.prefetch(img_host, heatmap_host): the next batch's H2D runs on a "
+                      "copy stream under the current step, the loss read-back is blocking"),
         gpu_launches=int(eng.launches_per_train_step() * args.steps),
+        loss_first_step=loss_first, loss_oracle=loss_oracle,
+        loss_rel_err=(abs(loss_first - loss_oracle) / abs(loss_oracle)) if isinstance(loss_oracle, float) else None,
+        strong_scaling=strong, e2e_module_api=module_api,
         roofline=dict(bound="hbm", achieved=dom["achieved"], peak=dom["peak"], unit="GB/s", frac=dom["frac"],
                       traffic=traffic, traffic_source=traffic_src, kernel=dom["kernel"], op=dom["op"], us_per_launch=dom["us"],
                       algorithmic_bytes=dom["bytes"], peak_source=pk["source"],
@@ -351,7 +469,7 @@ def main():
         # (oversubscribed cores) can only cost a bounded amount of time
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
-                                  "--cpu-sample", str(args.cpu_sample), "--steps", "2"] +
+                                  "--cpu-sample", str(args.cpu_sample), "--steps", "3"] +
                                  (["--dtype", args.dtype] if args.dtype else []) +
                                  (["--batch", str(args.batch)] if args.batch else []),
                                  capture_output=True, text=True, timeout=240).stdout

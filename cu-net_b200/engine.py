@@ -69,8 +69,12 @@ class Engine(object):
             else:
                 self.cnt_idx[s.name] = len(self.cnt_idx)
         self.n_params = off
+        # flat buffers are padded to a multiple of 64 elements so that they split evenly over 1/2/4/8/16 ranks into
+        # 16-byte-aligned shards (reduce-scatter -> shard RMSprop -> all-gather variant of the optimizer step)
+        off = (off + 63) // 64 * 64
+        self.n_params_padded = off
         if share is not None:
-            assert share.n_params == off and share.dtype == self.dtype
+            assert share.n_params_padded == off and share.dtype == self.dtype
             self.params, self.grads, self.sq_avg = share.params, share.grads, share.sq_avg
             self.bnbuf, self.counters, self.lr = share.bnbuf, share.counters, share.lr
         else:
@@ -414,10 +418,14 @@ class Engine(object):
         ev.record(side)
         main.wait_event(ev)
 
-    def optimizer_step(self, alpha=0.99, eps=1e-8):
+    def optimizer_step(self, alpha=0.99, eps=1e-8, start=0, end=None, grads=None):
+        """RMSprop on elements [start, end) of the flat buffers; ``grads`` (default: the same slice of the gradient
+        bucket) may be a separate buffer of end - start elements (the reduce-scattered shard)."""
         lib = L.load()
-        L.check(lib.cunet_rmsprop_step(C.c_void_p(self.params.data_ptr()), C.c_void_p(self.grads.data_ptr()),
-                                       C.c_void_p(self.sq_avg.data_ptr()), C.c_long(self.n_params),
+        end = self.n_params if end is None else end
+        gptr = (self.grads.data_ptr() + 4 * start) if grads is None else grads.data_ptr()
+        L.check(lib.cunet_rmsprop_step(C.c_void_p(self.params.data_ptr() + 4 * start), C.c_void_p(gptr),
+                                       C.c_void_p(self.sq_avg.data_ptr() + 4 * start), C.c_long(end - start),
                                        C.c_void_p(self.lr.data_ptr()), C.c_float(alpha), C.c_float(eps),
                                        L.stream_ptr()), "rmsprop_step")
 
@@ -449,7 +457,7 @@ class Trainer(object):
     """
 
     def __init__(self, net, batch, lr=2.5e-4, alpha=0.99, eps=1e-8, device=None, process_group=None,
-                 world_size=1, use_graph=False, quant=None):
+                 world_size=1, use_graph=False, quant=None, shard_optimizer=False, rank=0):
         """quant: optional BinOp / QuanOp built on ``net`` -- the step then follows the reference's quantized
         protocol (cu-net-prev-version-bin.py:163-191): quantize -> fwd/bwd -> restore -> fix grads -> step."""
         self.net = net
@@ -461,7 +469,18 @@ class Trainer(object):
         self.pg, self.world = process_group, world_size
         self.eng.grad_scale = 1.0 / world_size
         self.use_graph = use_graph
+        # reduce-scatter -> RMSprop on this rank's 1/world slice -> all-gather of the updated
+        # parameters, instead of allreduce -> replicated RMSprop (same bytes on the wire, 1/world of the optimizer
+        # work and state traffic per GPU).  The quantized protocol needs the full reduced gradient of every target
+        # tensor before the update, so it keeps the allreduce form.
+        self.shard_optimizer = bool(shard_optimizer) and world_size > 1 and quant is None
+        self.rank = rank
+        if self.shard_optimizer:
+            from .parallel import shard_range
+            self._sh0, self._sh1 = shard_range(self.eng.n_params_padded, rank, world_size)
+            self._gshard = torch.zeros(self._sh1 - self._sh0, device=self.eng.device)
         self._g_fb = self._g_opt = None
+        self._stage = self._staged = self._copy_stream = None     # prefetch() staging (double-buffered H2D)
         self.probe = None            # optional (name -> [start_event, end_event]) instrumentation, see bench.py
 
     def set_lr(self, lr):
@@ -472,17 +491,65 @@ class Trainer(object):
         self.eng.img.copy_(img, non_blocking=True)
         self.eng.target.copy_(heatmap, non_blocking=True)
 
-    def _fwd_bwd(self):
+    def prefetch(self, img, heatmap):
+        """Start the host -> device copy of the NEXT step's batch on a copy stream, into the staging buffers the next
+        train_step() / eval_step() will consume (call it right after launching the current step: the copy then
+        overlaps the step's kernels instead of preceding them).  Two staging sets alternate, so a prefetch never
+        overwrites a batch that a launched step has not consumed yet."""
         e = self.eng
+        if self._stage is None:
+            self._copy_stream = torch.cuda.Stream(device=e.device)
+            self._stage = [(torch.empty_like(e.img), torch.empty_like(e.target), torch.cuda.Event(), torch.cuda.Event())
+                           for _ in range(2)]
+            self._stage_next = 0
+        simg, stgt, ready, consumed = self._stage[self._stage_next]
+        cs = self._copy_stream
+        cs.wait_event(consumed)              # the step that used this staging set two prefetches ago has read it
+        with torch.cuda.stream(cs):
+            simg.copy_(img, non_blocking=True)
+            stgt.copy_(heatmap, non_blocking=True)
+            ready.record(cs)
+        self._staged = self._stage_next
+        self._stage_next ^= 1
+
+    def _consume_staged(self):
+        if self._staged is None:
+            return
+        simg, stgt, ready, consumed = self._stage[self._staged]
+        main = torch.cuda.current_stream()
+        main.wait_event(ready)
+        self.eng.img.copy_(simg, non_blocking=True)          # device -> device, ~20 us
+        self.eng.target.copy_(stgt, non_blocking=True)
+        consumed.record(main)
+        self._staged = None
+
+    def _quant_fwd(self):
         q = self.quant
         if q is not None:
             (q.binarization if hasattr(q, "binarization") else q.quantization)()
-        e.forward(train=True)
-        e.loss_and_decode(with_grad=True)
-        e.backward()
+
+    def _quant_bwd(self):
+        """restore + gradient fix-up of the quantized protocol (cu-net-prev-version-bin.py:189-190).  Runs AFTER the
+        gradient allreduce, like the reference (DataParallel reduces the replica gradients inside backward(), then
+        updateQuanGradWeight sees the reduced gradient): QuanOp's clip + round is not linear in the gradient."""
+        q = self.quant
         if q is not None:
             q.restore()
             (q.updateBinaryGradWeight if hasattr(q, "updateBinaryGradWeight") else q.updateQuanGradWeight)()
+
+    def _fwd_bwd(self):
+        e = self.eng
+        self._quant_fwd()
+        e.forward(train=True)
+        e.loss_and_decode(with_grad=True)
+        e.backward()
+
+    def _opt(self):
+        self._quant_bwd()
+        if self.shard_optimizer:
+            self.eng.optimizer_step(self.alpha, self.eps, self._sh0, self._sh1, grads=self._gshard)
+        else:
+            self.eng.optimizer_step(self.alpha, self.eps)
 
     def _capture(self):
         # warm-up on a side stream (sets kernel attributes, allocates nothing afterwards), then capture
@@ -490,7 +557,7 @@ class Trainer(object):
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self._fwd_bwd()
-            self.eng.optimizer_step(self.alpha, self.eps)
+            self._opt()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._g_fb = torch.cuda.CUDAGraph()
@@ -498,25 +565,43 @@ class Trainer(object):
             self._fwd_bwd()
         self._g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g_opt):
-            self.eng.optimizer_step(self.alpha, self.eps)
+            self._opt()
+
+    def _reduce_and_step(self):
+        """Gradient exchange + optimizer: allreduce -> replicated RMSprop, or (shard_optimizer) reduce-scatter ->
+        RMSprop on this rank's slice -> all-gather of the updated parameters."""
+        e = self.eng
+        if self.shard_optimizer:
+            from .parallel import reduce_scatter_mean, all_gather_params
+            reduce_scatter_mean(e.grads, self._gshard, self.world, self.pg)
+        elif self.world > 1:
+            from .parallel import allreduce_mean
+            allreduce_mean(e.grads, self.world, self.pg)  # gradients were pre-scaled by 1/world (sum == mean)
+        if self.use_graph:
+            if self._g_opt is None:
+                self._capture()
+            self._g_opt.replay()
+        else:
+            self._opt()
+        if self.shard_optimizer:
+            all_gather_params(e.params, e.params[self._sh0:self._sh1], self.world, self.pg)
 
     def train_step(self, img=None, heatmap=None):
+        """One training step.  Inputs: ``img`` / ``heatmap`` given (copied now, on the current stream), or staged
+        earlier by prefetch(), or already resident in the engine's input buffers."""
         e = self.eng
         if img is not None:
+            self._staged = None
             self.load_batch(img, heatmap)
+        else:
+            self._consume_staged()
         if self.use_graph:
             if self._g_fb is None:
                 self._capture()
             self._g_fb.replay()
         else:
             self._fwd_bwd()
-        if self.world > 1:
-            from .parallel import allreduce_mean
-            allreduce_mean(e.grads, self.world, self.pg)  # gradients were pre-scaled by 1/world (sum == mean)
-        if self.use_graph:
-            self._g_opt.replay()
-        else:
-            e.optimizer_step(self.alpha, self.eps)
+        self._reduce_and_step()
         return e.loss_value()
 
     def eval_step_flip(self, img=None, heatmap=None, flip_index=None):
@@ -548,7 +633,10 @@ class Trainer(object):
     def eval_step(self, img=None, heatmap=None):
         e = self.eng
         if img is not None:
+            self._staged = None
             self.load_batch(img, heatmap)
+        else:
+            self._consume_staged()
         e.forward(train=False)
         e.loss_and_decode(with_grad=False)
         return e.loss_value(), e.preds

@@ -41,3 +41,33 @@ def broadcast_params(flat, world, group=None, src=0):
         import torch.distributed as dist
         dist.broadcast(flat, src, group=group)
     return flat
+
+
+def shard_range(n, rank, world):
+    """[start, end) of rank's slice of a flat buffer of n elements (n is padded to a multiple of world by the
+    engine, see Engine.n_params_padded)."""
+    if n % world:
+        raise ValueError("flat buffer of %d elements is not divisible by %d ranks" % (n, world))
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+def reduce_scatter_mean(flat, shard_out, world, group=None):
+    """the gradient exchange as reduce-scatter -- every rank receives only the summed slice
+    it will update (gradients pre-scaled by 1/world: sum == mean).  shard_out: [n / world]."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.reduce_scatter_tensor(shard_out, flat, op=dist.ReduceOp.SUM, group=group)
+    else:
+        shard_out.copy_(flat)
+    return shard_out
+
+
+def all_gather_params(flat, shard, world, group=None):
+    """The updated parameter slices back into every rank's full flat parameter buffer."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(flat, shard, group=group)
+    else:
+        flat.copy_(shard)
+    return flat

@@ -131,6 +131,10 @@ class Plan(object):
                              "neck_size=4, growth_rate=32, init_chan_num=128 (cu-net.py:46)")
         if in_res % 64:
             raise ValueError("input resolution must be a multiple of 64")
+        if order + 3 > 8:
+            # widest virtual concat = an up-block adapter: [U, S, O_{i-K} .. O_i] = K + 3 segments (CUNET_MAX_SEG = 8)
+            raise ValueError("order %d needs %d concat segments per conv; the kernels take at most 8 (order <= 5)"
+                             % (order, order + 3))
         self.class_num, self.L, self.K, self.loss_num = class_num, layer_num, order, loss_num
         self.g, self.C0, self.bott = growth_rate, init_chan_num, neck_size * growth_rate
         self.in_res, self.stem_res, self.out_res = in_res, in_res // 2, in_res // 4

@@ -9,16 +9,52 @@ import torch
 from oracle import ref_loader
 
 
-class _History(object):
-    """Minimal stand-in for utils/train_history.TrainHistory: what Checkpoint touches."""
-    def __init__(self, lr=2.5e-4, epoch=3):
-        self.lr, self.epoch, self.is_best = [{"lr": lr}], [{"epoch": epoch}], True
+def _History(lr=2.5e-4, epoch=3):
+    """The product's TrainHistory (drop-in for utils/util.py:8-46) holding one epoch record."""
+    from collections import OrderedDict
+    from cunet_b200.utils.util import TrainHistory
+    h = TrainHistory()
+    h.update(OrderedDict([("epoch", epoch)]), OrderedDict([("lr", lr)]),
+             OrderedDict([("train_loss", 0.5), ("val_loss", 0.6)]), OrderedDict([("val_pckh", 0.25)]))
+    return h
 
-    def state_dict(self):
-        return {"lr": self.lr, "epoch": self.epoch}
 
-    def load_state_dict(self, sd):
-        self.lr, self.epoch = sd["lr"], sd["epoch"]
+def _reference_train_history_class():
+    """The REAL TrainHistory class (utils/util.py:8-46): only the class text is executed (the module imports PIL /
+    visdom-era helpers that are irrelevant here)."""
+    from collections import OrderedDict
+    src = open(os.path.join(ref_loader.REF_ROOT, "utils", "util.py")).read()
+    start, end = src.index("class TrainHistory():"), src.index("class TrainHistoryFace():")
+    ns = {"OrderedDict": OrderedDict}
+    exec(src[start:end], ns)
+    return ns["TrainHistory"]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_train_history_round_trips_with_the_reference_class(tmp_path):
+    """A checkpoint's 'train_history' written here loads in the reference's TrainHistory.load_state_dict
+    (utils/util.py:40-46: epoch, lr, loss, pckh, best_pckh, is_best) and vice versa, with identical bookkeeping."""
+    from collections import OrderedDict
+    from cunet_b200.utils.util import TrainHistory
+    Ref = _reference_train_history_class()
+    ours, ref = TrainHistory(), Ref()
+    for e, (pck, lr) in enumerate([(0.1, 1e-3), (0.3, 1e-3), (0.2, 5e-4)]):
+        args = (OrderedDict([("epoch", e)]), OrderedDict([("lr", lr)]),
+                OrderedDict([("train_loss", 1.0 / (e + 1)), ("val_loss", 2.0 / (e + 1))]), OrderedDict([("val_pckh", pck)]))
+        ours.update(*args)
+        ref.update(*args)
+        assert ours.is_best == ref.is_best and ours.best_pckh == ref.best_pckh
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    assert ours.state_dict() == ref.state_dict()
+    path = str(tmp_path / "h.pt")
+    torch.save({"train_history": ours.state_dict()}, path)
+    back = Ref()
+    back.load_state_dict(torch.load(path, weights_only=False)["train_history"])        # KeyError before this round
+    assert back.state_dict() == ref.state_dict()
+    mine = TrainHistory()
+    mine.load_state_dict(ref.state_dict())
+    assert mine.state_dict() == ours.state_dict() and mine.last_epoch() == 2
+    assert TrainHistory().last_epoch() == -1                                            # empty: no sentinel records
 
 
 def _nets(class_num=5, layer_num=3, order=1, loss_num=2):
@@ -99,8 +135,7 @@ def test_entry_point_resume(tmp_path):
     from cunet_b200.models.cu_net import create_cu_net
     from cunet_b200.utils.checkpoint import Checkpoint
     a = create_cu_net(4, 32, 128, 3, 2, 1, 2)
-    hist = entry.TrainHistory(1e-3)
-    hist.update(5e-4, 11)
+    hist = _History(5e-4, 11)
     os.makedirs(str(tmp_path / "run1"))
     ck = Checkpoint()
     ck.save_prefix = str(tmp_path / "run1") + os.sep
@@ -109,9 +144,10 @@ def test_entry_point_resume(tmp_path):
     opt = entry.parse(["--exp_dir", str(tmp_path), "--exp_id", "run1", "--layer_num", "2", "--class_num", "3",
                        "--resume_prefix", os.path.basename(path)])
     b = create_cu_net(4, 32, 128, 3, 2, 1, 2)
-    hist_b = entry.TrainHistory(opt.lr)
+    hist_b = entry.TrainHistory()
     state = entry.resume(b, opt, hist_b)
-    assert opt.lr == 5e-4 and hist_b.epoch[-1]["epoch"] == 11 and "param_groups" in state
+    assert opt.lr == 5e-4 and hist_b.last_epoch() == 11 and "param_groups" in state
+    assert hist_b.pckh[-1]["val_pckh"] == 0.25 and hist_b.loss[-1]["val_loss"] == 0.6 and hist_b.best_pckh == 0.25
     for k, v in b.state_dict().items():
         assert torch.equal(v, a.state_dict()[k]), k
 

@@ -1,0 +1,144 @@
+"""Model-level checks on the configurations bench.py runs (BASELINE.json configs[1] and configs[2]) at their FULL batch.
+
+  * configs[2]  CU-Net-8 / bf16 / batch 24 -- the headline number: loss against the CPU oracle, per-head deviation
+    against what bf16 activation storage alone does to the fp32 oracle (tests/test_sensitivity_cpu.py's experiment at
+    L=8), and the bf16 parameter gradients against the fp32 CUDA path on the same inputs and weights.
+  * configs[1]  CU-Net-2 / fp32 / batch 24 -- the parity configuration: heads and loss within 1e-3 of the fp32 oracle,
+    gradients against the exact float64 oracle at the batch the bench runs (where BatchNorm statistics are taken over
+    24 x 64 x 64 samples instead of 2 x 64 x 64 and the problem is correspondingly better conditioned).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cunet_oracle, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _rms(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30)).item()
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-20)).item()
+
+
+def _cuda_run(class_num, L, K, loss_num, n, dtype, state, img, hm):
+    """forward + multi-loss MSE + backward through the reference-facing module API; returns heads, loss, grads."""
+    from cunet_b200.models.cu_net import create_cu_net
+    net = create_cu_net(4, 32, 128, class_num, L, K, loss_num, dtype=dtype)
+    net.engine(n, "cuda:0")
+    net.load_state_dict(state)
+    net.train()
+    outs = net(img.cuda())
+    loss = cunet_oracle.multi_loss_mse(outs, hm.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().float().cpu().clone() for k, p in net.named_parameters()}
+    heads = [o.detach().float().cpu() for o in outs]
+    del net
+    torch.cuda.empty_cache()
+    return heads, float(loss.detach()), grads
+
+
+def headline_report(n=24, L=8, class_num=68):
+    """All the numbers of the CU-Net-8 / bf16 / batch-24 check (also printed by tools/headline_parity.py)."""
+    K, loss_num = 1, L
+    state = cunet_oracle.init_state(class_num, L, K, seed=0)
+    img, hm = synthetic.make_inputs(n, class_num, seed=0)
+    torch.set_num_threads(min(torch.get_num_threads(), 32))
+    with torch.no_grad():
+        ref = cunet_oracle.OracleCUNet(state, class_num, L, K, loss_num)(img)
+        oloss = float(cunet_oracle.multi_loss_mse(ref, hm))
+        # what bf16 STORAGE of the conv outputs alone does inside the fp32 oracle (the heads stay fp32)
+        orig = F.conv2d
+
+        def conv(x, w, *a, **k):
+            y = orig(x, w, *a, **k)
+            return y.bfloat16().float() if w.shape[0] in (128, 32) else y
+        cunet_oracle.F.conv2d = conv
+        try:
+            pert = cunet_oracle.OracleCUNet(state, class_num, L, K, loss_num)(img)
+        finally:
+            cunet_oracle.F.conv2d = orig
+    predicted = [_rms(a, b) for a, b in zip(pert, ref)]
+    h16, l16, g16 = _cuda_run(class_num, L, K, loss_num, n, "bf16", state, img, hm)
+    h32, l32, g32 = _cuda_run(class_num, L, K, loss_num, n, "fp32", state, img, hm)
+    cos, rel = {}, {}
+    for k, g in g32.items():
+        if g.numel() >= 64 and g.abs().max() > 0:
+            cos[k] = F.cosine_similarity(g16[k].flatten().double(), g.flatten().double(), dim=0).item()
+            rel[k] = ((g16[k].double() - g.double()).norm() / g.double().norm()).item()
+    cs, rs = sorted(cos.values()), sorted(rel.values())
+    return dict(loss_oracle=oloss, loss_bf16=l16, loss_fp32=l32,
+                head_rms_bf16=[_rms(a, b) for a, b in zip(h16, ref)],
+                head_rms_fp32=[_rms(a, b) for a, b in zip(h32, ref)],
+                head_rms_predicted=predicted,
+                grad_cos_min=cs[0], grad_cos_p10=cs[len(cs) // 10], grad_cos_median=cs[len(cs) // 2],
+                grad_rel_median=rs[len(rs) // 2], grad_rel_p90=rs[int(len(rs) * 0.9)], grad_rel_max=rs[-1],
+                worst=min(cos, key=cos.get), n_tensors=len(cs),
+                finite=all(torch.isfinite(g).all().item() for g in g16.values()))
+
+
+def test_cunet8_bf16_batch24_headline_config():
+    r = headline_report()
+    print("headline parity:", r)
+    assert r["finite"]
+    # north_star's bar applies to fp32 storage: the fp32 CUDA path on the headline model
+    assert abs(r["loss_fp32"] - r["loss_oracle"]) < 1e-3 * abs(r["loss_oracle"])
+    # bf16: the loss within 1e-2 of the CPU oracle, every head within 2x of what bf16 storage alone does to the oracle
+    assert abs(r["loss_bf16"] - r["loss_oracle"]) < 1e-2 * abs(r["loss_oracle"])
+    for got, pred in zip(r["head_rms_bf16"], r["head_rms_predicted"]):
+        assert got < max(2.0 * pred, 0.02), (r["head_rms_bf16"], r["head_rms_predicted"])
+    # bf16 parameter gradients against the fp32 CUDA path (same inputs, same weights)
+    assert r["grad_cos_median"] > 0.98 and r["grad_cos_p10"] > 0.9, r
+    assert r["grad_rel_median"] < 0.2, r
+
+
+def parity24_report(n=24):
+    class_num, L, K, loss_num = 68, 2, 1, 2
+    state = cunet_oracle.init_state(class_num, L, K, seed=0)
+    img, hm = synthetic.make_inputs(n, class_num, seed=0)
+    torch.set_num_threads(min(torch.get_num_threads(), 32))
+    ora = cunet_oracle.OracleCUNet(state, class_num, L, K, loss_num)
+    oouts = ora(img)
+    oloss = cunet_oracle.multi_loss_mse(oouts, hm)
+    oloss.backward()
+    o64 = cunet_oracle.OracleCUNet({k: v.double() if v.is_floating_point() else v for k, v in state.items()},
+                                   class_num, L, K, loss_num)
+    for nme in o64.param_names:
+        o64.state[nme] = o64.state[nme].detach().double().requires_grad_(True)
+    outs64 = o64(img.double())
+    cunet_oracle.multi_loss_mse(outs64, hm.double()).backward()
+    heads, loss, grads = _cuda_run(class_num, L, K, loss_num, n, "fp32", state, img, hm)
+    mine, o32, cos = [], [], []
+    for name in ora.param_names:
+        g64 = o64.state[name].grad
+        if g64 is None:
+            continue
+        mine.append(_rel(grads[name], g64))
+        o32.append(_rel(ora.state[name].grad, g64))
+        if g64.numel() >= 64:
+            cos.append(F.cosine_similarity(grads[name].flatten().double(), g64.flatten(), dim=0).item())
+    mine.sort()
+    o32.sort()
+    return dict(head_rel=[_rel(a, b.detach()) for a, b in zip(heads, oouts)],
+                head_rel64=[_rel(a, b.detach()) for a, b in zip(heads, outs64)],
+                oracle32_head_rel64=[_rel(a.detach(), b.detach()) for a, b in zip(oouts, outs64)],
+                loss=loss, loss_oracle=float(oloss.detach()),
+                grad_med=mine[len(mine) // 2], grad_p90=mine[int(len(mine) * 0.9)], grad_max=mine[-1],
+                o32_grad_med=o32[len(o32) // 2], o32_grad_p90=o32[int(len(o32) * 0.9)], o32_grad_max=o32[-1],
+                cos_min=min(cos))
+
+
+def test_cunet2_fp32_batch24_parity_config():
+    """BASELINE.json configs[1] at its real batch: 1e-3 on heads and loss; gradients vs the exact float64 oracle."""
+    r = parity24_report()
+    print("config-2 parity:", r)
+    assert max(r["head_rel"]) < 1e-3, r
+    assert abs(r["loss"] - r["loss_oracle"]) < 1e-3 * abs(r["loss_oracle"])
+    assert r["cos_min"] > 0.995, r
+    assert r["grad_med"] < max(1e-3, 3 * r["o32_grad_med"]), r
+    assert r["grad_p90"] < max(3e-3, 3 * r["o32_grad_p90"]), r

@@ -36,5 +36,27 @@ if rank == 0:
         acc += e.grads / world
     err = ((got - acc).abs().max() / acc.abs().max()).item()
     print("DP_CHECK world=%d rel err %.3e %s" % (world, err, "OK" if err < 2e-3 else "FAIL"))
+# reduce-scatter -> shard RMSprop -> all-gather == allreduce -> replicated RMSprop, from the
+# same parameters / optimizer state / per-rank gradients
+e.grad_scale = 1.0 / world
+p0, v0 = e.params.clone(), e.sq_avg.clone()
+gen = torch.Generator(device="cpu").manual_seed(100 + rank)
+g_local = (torch.randn(e.grads.numel(), generator=gen) * 1e-3).to(dev)
+e.grads.copy_(g_local)
+tr._reduce_and_step()
+torch.cuda.synchronize()
+pA, vA = e.params.clone(), e.sq_avg.clone()
+e.params.copy_(p0); e.sq_avg.copy_(v0); e.grads.copy_(g_local)
+tr2 = Trainer(net, bs, lr=1e-3, device=dev, process_group=dist.group.WORLD, world_size=world, shard_optimizer=True,
+              rank=rank)
+tr2._reduce_and_step()
+torch.cuda.synchronize()
+s0, s1 = tr2._sh0, tr2._sh1
+same_p = torch.equal(e.params, pA)
+same_v = torch.equal(e.sq_avg[s0:s1], vA[s0:s1])           # the optimizer state only exists for the rank's slice
+flag = torch.tensor([int(same_p and same_v)], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("SHARD_OPT_CHECK world=%d params identical on every rank: %s" % (world, "OK" if int(flag) else "FAIL"))
 dist.barrier()
 dist.destroy_process_group()
