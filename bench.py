@@ -386,11 +386,15 @@ def main():
     plan = eng.plan
     pk = peaks()
     probe_op = max(plan.ops, key=lambda o: (o.cin * o.cout * o.res * o.res, o.index))
-    kinds = ["fwd", "dgrad", "wgrad"]
+    # large 1x1 ops run their backward as ONE fused dgrad+wgrad launch (csrc/conv_bwd1x1.cu): it is probed as "bwd"
+    # with the bytes of the backward-data contract (G/T of the output, every source, every source gradient) -- the
+    # filter gradient adds no HBM traffic of its own
+    fused_bwd = eng.is_fused_1x1(probe_op)
+    kinds = ["fwd", "bwd"] if fused_bwd else ["fwd", "dgrad", "wgrad"]
     eng.probes = {}
     evs = {}
     for k in kinds:
-        prm = eng.call_index[(probe_op.name, k)]
+        prm = eng.call_index[(probe_op.name, "dgrad" if k == "bwd" else k)]
         evs[k] = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
         eng.probes[id(prm)] = evs[k]
     acc = {k: [] for k in kinds}
@@ -404,18 +408,18 @@ def main():
     roofs = {}
     for k in kinds:
         t_ms = sorted(acc[k])[len(acc[k]) // 2]
-        by = op_bytes(eng, probe_op, k)
-        flops = 2.0 * eng.N * probe_op.res ** 2 * probe_op.cin * probe_op.cout * probe_op.taps
-        roofs[k] = dict(kernel="conv_%s" % k, op=probe_op.name, us=1000.0 * t_ms, bytes=by,
+        by = op_bytes(eng, probe_op, "dgrad" if k == "bwd" else k)
+        flops = 2.0 * eng.N * probe_op.res ** 2 * probe_op.cin * probe_op.cout * probe_op.taps * (2 if k == "bwd" else 1)
+        roofs[k] = dict(kernel="conv_bwd1x1 (fused dgrad+wgrad)" if k == "bwd" else "conv_%s" % k, op=probe_op.name, us=1000.0 * t_ms, bytes=by,
                         achieved=by / (t_ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
                         frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm"], tflops=flops / (t_ms * 1e-3) / 1e12)
-    dom = roofs["dgrad"]
+    dom = roofs["bwd" if fused_bwd else "dgrad"]
     # DRAM traffic of the dominant kernel on this op: dram__bytes_read.sum + dram__bytes_write.sum of the committed
     # `ncu --set full` capture (profiles/traffic.json names the capture); not measurable from inside this process
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and cfg["dtype"] == "bf16":
-        tj = json.load(open(tpath)).get("conv_dgrad")
+        tj = json.load(open(tpath)).get("conv_bwd1x1" if fused_bwd else "conv_dgrad")
         if tj:
             # the capture is only quoted while the kernel source it was taken from is unchanged (sha1 of the .cu file)
             import hashlib

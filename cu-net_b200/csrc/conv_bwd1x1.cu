@@ -1,0 +1,830 @@
+// Fused backward of the 1x1 fused conv (cat -> BN -> ReLU -> conv1x1 [-> pool]; adapters, bottleneck conv1,
+// intermedia adapters, heat-map heads; bf16): backward-data AND backward-filter in ONE persistent kernel.
+// Same math as cunet_conv_dgrad + cunet_conv_wgrad for taps == 1 (see conv_dgrad.cu / conv_wgrad.cu):
+//
+//   dgrad : dA[p][k]   = sum_co dT[p][co] * W[co][k]      then per source: dz = dA * [bn(x) > 0], dgamma / dbeta,
+//                                                          G_src += gamma * dz (4-child sum for an upsampled source)
+//   wgrad : dW[co][k] += sum_p  a[p][k]  * dT[p][co],      a = relu(bn(x))
+//
+// Both contractions consume the SAME gradient operand dT (the SWIZZLE_128B row tile [64 px][128 co] is a K-major
+// operand for the first and an MN-major operand for the second -- common.cuh) and the SAME landed input x, which the
+// round-1 pair of kernels (conv_dgrad_v2 + conv_wgrad_v2) each fetched from HBM and transformed on their own, in two
+// launches that both wanted all 148 SMs.  Here, per stage of 64 pixels:
+//   * G / T (/ pool argmax) of the output and every source piece of the virtual concat are contiguous blocks of NHWC
+//     tensors: 1-D TMA bulk copies land them in shared memory (x double buffered, landed ONCE for both contractions);
+//   * 8 transformer warps build dT = a*G + b*(T - mu) + d (batch-norm backward form, pool routing) and, per
+//     128-channel chunk, a = relu(bn(x)), smem -> smem, as swizzled operand tiles;
+//   * one thread issues  D1_c[128 k][64 px]   = Wimg_c[128 k][Cout] * dT^T       (fresh per (stage, chunk), TMEM
+//                                                                                 double buffered)
+//                        D2_c[128 k][Cout]   += A_c^T[128 k][64 px] * dT          (TMEM resident for the CTA's whole
+//                                                                                 pixel range, one per chunk);
+//     the dgrad weight image of the whole conv (<= 96 KB) stays resident in shared memory;
+//   * 8 epilogue warps (thread = input channel = TMEM lane, wide tcgen05.ld) apply the ReLU mask, keep dbeta / dgamma
+//     in registers and overwrite x IN PLACE with gamma*dz; one thread bulk-stores (or L2-reduce-adds) the pieces;
+//   * at the end D2 is added to the fp32 weight gradient with coalesced red.global.add.
+// Stage geometry: 64 consecutive raster pixels, except for 64-wide images with an upsampled source, where a stage is
+// 2 rows x 32 columns (two runs of 32 pixels) so that every 2x2 window of the half-resolution source is complete
+// inside one stage (its four children are summed in the epilogue).
+// HBM traffic per launch = G, T of the output + every source once + every source gradient once.
+#include "loaders.cuh"
+#include "host_util.h"
+#include <stdlib.h>
+
+namespace cunet {
+
+// warp 0 landing producer | 1 store issuer | 2 dgrad MMA issuer | 3 wgrad MMA issuer | 4-11 transformers | 12-27 epilogue.
+// 16 epilogue warps (four per TMEM lane quarter, 16 pixels each): the epilogue is a chain of dependent shared-memory
+// round trips per pixel, and with only two warps per scheduler the first version of this kernel spent 1.7 us per
+// 128-channel chunk of a 64-pixel stage waiting on instruction latency (in-kernel timeline, tools/time_bwd1x1.py).
+constexpr int F1_THREADS = 896;
+constexpr int F1_R = 64;         // pixels per stage
+constexpr int F1_SUB = F1_R * 128;  // one operand sub-tile: 64 rows x 128 B
+constexpr int F1_GT_BYTES = 32768;  // one G/T landing set: G at +0, T at +16384, pool argmax bytes at +24576
+constexpr int F1_MAXCH = 3;      // 128-channel chunks (Cin <= 384)
+
+struct F1Layout {
+  int w_off, dt_off, a_off, gt_off, x_off, tail_off;
+  int x_bytes;      // one x buffer (all pieces of a stage)
+  int gt_bufs;      // 1 or 2 G/T landing sets
+  int split;        // 1: stage = 2 rows x 32 columns (64-wide image with an upsampled source)
+  int per;          // stages per CTA
+  int npad;         // gradient operand columns (Cout rounded up to 64)
+  int dwc;          // row length of dw
+  float* dw;
+};
+
+struct F1Tail {
+  alignas(16) uint32_t sc2[MAX_CIN / 2];   // bf16x2 BatchNorm scale / shift of the concat (transformers)
+  alignas(16) uint32_t sh2[MAX_CIN / 2];
+  alignas(16) uint32_t ga2[64], gb2[64], gmu2[64], gd2[64];   // bf16x2 gradient-form coefficients (GradSmem packed)
+  uint64_t w_full, dt_ready, dt_free, done;
+  uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[2], d1_free[2], a_full[2], a_free[2];
+  uint64_t a_done[2][F1_MAXCH], g_ready[2][F1_MAXCH];
+  uint32_t tmem_base;
+  int seg_start[CUNET_MAX_SEG + 1];
+  int xoff[CUNET_MAX_SEG];     // byte offset of segment s's piece inside an x buffer
+  int woff[F1_MAXCH + 1];      // byte offset of chunk c's weight rows inside the resident image
+  int lowmap[F1_R];            // stage row -> row of the half-resolution run
+  int rowpos[F1_R];            // stage row -> position inside its 2x2 window ((h & 1) * 2 + (w & 1))
+};
+
+__device__ __forceinline__ void f1_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void f1_bulk_red_add_bf16(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void f1_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void f1_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ float f1_lds_bf16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return __uint_as_float((uint32_t)v << 16);
+}
+__device__ __forceinline__ void f1_sts_u16(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint4 f1_lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint2 f1_lds64(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread; the wait is separate so that two loads can be
+// in flight before the first use
+__device__ __forceinline__ void f1_tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void f1_tmem_ld8_nowait(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void f1_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void f1_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// geometry of one stage: first pixel of run 0 / run 1 (split only), valid pixel count, half-resolution run
+struct F1Geo {
+  int p0, p1, nv, low0, nlow;
+};
+__device__ __forceinline__ F1Geo f1_geo(int st, int M, int W, int split, int need_low) {
+  F1Geo g;
+  if (split) {                       // W == 64: row pair a = st >> 1, column half b = st & 1
+    const int a = st >> 1, b = st & 1;
+    g.p0 = a * 128 + 32 * b;
+    g.p1 = g.p0 + 64;
+    g.nv = 64;
+    g.low0 = a * 32 + 16 * b;
+    g.nlow = 16;
+  } else {
+    g.p0 = st * F1_R;
+    g.p1 = -1;
+    g.nv = min(F1_R, M - g.p0);
+    g.low0 = 0;
+    g.nlow = 0;
+    if (need_low) {
+      if (W == 64) {                 // one image row: its half-resolution row (H is even)
+        g.low0 = ((g.p0 >> 6) >> 1) * 32;
+        g.nlow = 32;
+      } else {                       // whole row pairs (W <= 32): low pixels of the block are consecutive
+        g.low0 = g.p0 >> 2;
+        g.nlow = g.nv >> 2;
+      }
+    }
+  }
+  return g;
+}
+
+// timeline slots (CUNET_TRACE builds), stage i < 12 of CTA 0: producer 0+2i (G/T issued, x issued), transformer 32+4i
+// (start, G/T landed + operand free, dT done, all chunk operands done), MMA 96+3i (dT ready, first D1 issued, stage
+// issued), epilogue 144+4i (chunk 0 accumulator full, chunk 0 done, last chunk done), store 200+2i; 230 / 231: dW
+// epilogue start / end
+CUNET_TRACE_DECL(g_f1_trace)
+
+__global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid_constant__ cunet_conv_dgrad_params p,
+                                                                     const __grid_constant__ F1Layout L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  F1Tail* tail = reinterpret_cast<F1Tail*>(smem + L.tail_off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, W = p.W;
+  const int M = p.N * H * W;
+  const int Cin = concat_cin(p.in);
+  const int nchunk = (Cin + 127) >> 7;
+  const int nkb = (p.CoutPad + 63) >> 6;
+  const int total = (M + F1_R - 1) / F1_R;
+  const int st0 = (int)blockIdx.x * L.per;
+  const int st1 = min(total, st0 + L.per);
+  const int ns = max(0, st1 - st0);
+  const int ldo = p.dy.ld * 2;
+  const int split = L.split;
+  int need_low = p.dy.pooled;
+  for (int s = 0; s < p.in.nseg; ++s) need_low |= p.in.seg[s].up;
+  CUNET_TRACE_LOAD(trace, g_f1_trace)
+
+  if (tid == 0) {
+    mbar_init(&tail->w_full, 1);
+    mbar_init(&tail->dt_ready, 8);
+    mbar_init(&tail->dt_free, 2);     // the dgrad and the wgrad MMA issuers both release the gradient operand
+    mbar_init(&tail->done, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->gt_full[b], 1);
+      mbar_init(&tail->gt_free[b], 8);
+      mbar_init(&tail->x_full[b], 1);
+      mbar_init(&tail->x_free[b], 1);
+      mbar_init(&tail->d1_full[b], 1);
+      mbar_init(&tail->d1_free[b], 16);
+      mbar_init(&tail->a_full[b], 8);
+      mbar_init(&tail->a_free[b], 1);
+      for (int c = 0; c < F1_MAXCH; ++c) {
+        mbar_init(&tail->a_done[b][c], 8);
+        mbar_init(&tail->g_ready[b][c], 16);
+      }
+    }
+    fence_mbar_init();
+    // static tables
+    int acc = 0, xo = 0;
+    for (int s = 0; s < p.in.nseg; ++s) {
+      tail->seg_start[s] = acc;
+      acc += p.in.seg[s].C;
+      tail->xoff[s] = xo;
+      xo += (p.in.seg[s].up ? 16 : F1_R) * p.in.seg[s].C * 2;   // an upsampled source contributes 16 low pixels
+    }
+    for (int s = p.in.nseg; s <= CUNET_MAX_SEG; ++s) tail->seg_start[s] = acc;
+    int wo = 0;
+    for (int c = 0; c <= F1_MAXCH; ++c) {
+      tail->woff[c] = wo;
+      if (c < nchunk) wo += min(128, Cin - c * 128) * 128 * nkb;
+    }
+  }
+  if (tid < F1_R) {
+    // stage row -> half-resolution row of the stage's low run, and position inside the 2x2 window
+    const int r = tid;
+    int lm = 0, ps = 0;
+    if (split) {
+      lm = (r & 31) >> 1;
+      ps = ((r >> 5) << 1) | (r & 1);
+    } else if (W == 64) {
+      lm = r >> 1;
+      ps = r & 1;                     // + 2 * (image row parity), added per stage
+    } else {
+      const int lw = 31 - __clz(W);
+      const int hl = r >> lw, w = r & (W - 1);
+      lm = (hl >> 1) * (W >> 1) + (w >> 1);
+      ps = ((hl & 1) << 1) | (w & 1);
+    }
+    tail->lowmap[r] = lm;
+    tail->rowpos[r] = ps;
+  }
+  if (warp == 2) tmem_alloc(&tail->tmem_base, 512);
+  griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
+  griddep_launch();
+  // BatchNorm / gradient coefficients: computed in the (not yet used) x landing area, then kept in registers per role
+  BnSmem* bn = reinterpret_cast<BnSmem*>(smem + L.x_off);
+  GradSmem* gc = reinterpret_cast<GradSmem*>(smem + L.x_off + 8192);
+  compute_bn_coefs(p.in, bn, nchunk * 128, tid, F1_THREADS);
+  compute_grad_coefs(p.dy, gc, tid, F1_THREADS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  const bool is_tr = warp >= 4 && warp < 12, is_ep = warp >= 12;
+  const int t = tid - 128;                 // transformer thread index (0..255)
+  const int cc = t & 15, rb = t >> 4;      // 16-byte column x rows rb + 16q
+  const int e = warp - 12;
+  const int qd = warp & 3, pq = (e >> 2) & 3;  // epilogue: TMEM lane quarter (hardware: warp % 4), pixel quarter
+  const int k = qd * 32 + lane;                // epilogue: channel inside the chunk
+  // transformer constants (coefficients stay in shared memory: tail->sc2 / sh2 / ga2 ...)
+  int cs_s[F1_MAXCH], cs_cl2[F1_MAXCH], cs_ldx[F1_MAXCH], cs_up[F1_MAXCH];
+  // epilogue constants
+  float e_sc[F1_MAXCH], e_sh[F1_MAXCH], e_is[F1_MAXCH], e_nmi[F1_MAXCH], e_gm[F1_MAXCH];
+  int e_ps[F1_MAXCH];
+#pragma unroll
+  for (int c = 0; c < F1_MAXCH; ++c) {
+    cs_s[c] = -1; cs_cl2[c] = 0; cs_ldx[c] = 0; cs_up[c] = 0;
+    e_sc[c] = e_sh[c] = e_is[c] = e_nmi[c] = e_gm[c] = 0.f;
+    e_ps[c] = -1;
+  }
+  // packed coefficient tables -> tail (they outlive the prologue area)
+  for (int i = tid; i < nchunk * 64; i += F1_THREADS) {
+    tail->sc2[i] = bn->sc2[i];
+    tail->sh2[i] = bn->sh2[i];
+  }
+  if (tid < 64) {
+    tail->ga2[tid] = gc->a2[tid];
+    tail->gb2[tid] = gc->b2[tid];
+    tail->gmu2[tid] = gc->mu2[tid];
+    tail->gd2[tid] = gc->d2[tid];
+  }
+  if (is_tr) {
+#pragma unroll
+    for (int c = 0; c < F1_MAXCH; ++c) {
+      const int ch = c * 128 + cc * 8;
+      if (c < nchunk && ch < Cin) {
+        int s = 0;
+        while (ch >= tail->seg_start[s + 1]) ++s;
+        cs_s[c] = s;
+        cs_cl2[c] = (ch - tail->seg_start[s]) * 2;
+        cs_ldx[c] = p.in.seg[s].C * 2;
+        cs_up[c] = p.in.seg[s].up;
+      }
+    }
+  }
+  if (is_ep) {
+#pragma unroll
+    for (int c = 0; c < F1_MAXCH; ++c) {
+      const int kg = c * 128 + k;
+      if (c < nchunk && kg < Cin) {
+        int s = 0;
+        while (kg >= tail->seg_start[s + 1]) ++s;
+        e_ps[c] = s;
+        e_sc[c] = bn->scale[kg];
+        e_sh[c] = bn->shift[kg];
+        e_is[c] = bn->istd[kg];
+        e_nmi[c] = -bn->mean[kg] * bn->istd[kg];  // xhat = x * istd - mean * istd
+        e_gm[c] = p.in.gamma[kg];
+      }
+    }
+  }
+  __syncthreads();    // the coefficient area is the x landing area from here on
+
+  if (warp == 0) {
+    // ============================================================== landing producer
+    if (lane == 0 && ns > 0) {
+      // resident dgrad weight image: per chunk and K block only the rows that hold real input channels
+      uint32_t wtot = 0;
+      for (int c = 0; c < nchunk; ++c) wtot += (uint32_t)(min(128, Cin - c * 128) * 128 * nkb);
+      mbar_arrive_expect_tx(&tail->w_full, wtot);
+      for (int c = 0; c < nchunk; ++c) {
+        const int rows = min(128, Cin - c * 128);
+        for (int kb = 0; kb < nkb; ++kb)
+          bulk_g2s(smem + L.w_off + tail->woff[c] + kb * rows * 128,
+                   reinterpret_cast<const char*>(p.wpack_dgrad) + ((size_t)c * nkb + kb) * 16384, (uint32_t)(rows * 128),
+                   &tail->w_full);
+      }
+      const char* gsrc = reinterpret_cast<const char*>(p.dy.g);
+      const char* tsrc = reinterpret_cast<const char*>(p.dy.t);
+      for (int i = 0; i < ns; ++i) {
+        const F1Geo g = f1_geo(st0 + i, M, W, split, need_low);
+        // ---- G / T (/ argmax) of the output
+        const int gbuf = L.gt_bufs == 2 ? (i & 1) : 0;
+        const uint32_t gu = (uint32_t)(L.gt_bufs == 2 ? (i >> 1) : i);
+        mbar_wait(&tail->gt_free[gbuf], (gu & 1u) ^ 1u);
+        if (i < 12) CUNET_TRACE_MARK(trace, 0 + 2 * i);
+        uint8_t* gdst = smem + L.gt_off + gbuf * F1_GT_BYTES;
+        if (p.dy.pooled) {
+          const uint32_t gb = (uint32_t)(g.nlow * ldo), ib = (uint32_t)(g.nlow * p.dy.C);
+          mbar_arrive_expect_tx(&tail->gt_full[gbuf], 2u * gb + ib);
+          bulk_g2s(gdst, gsrc + (long)g.low0 * ldo, gb, &tail->gt_full[gbuf]);
+          bulk_g2s(gdst + 16384, tsrc + (long)g.low0 * ldo, gb, &tail->gt_full[gbuf]);
+          bulk_g2s(gdst + 24576, p.dy.pool_idx + (long)g.low0 * p.dy.C, ib, &tail->gt_full[gbuf]);
+        } else {
+          const uint32_t nt = p.dy.mode == 1 ? 2u : 1u;
+          if (split) {
+            const uint32_t rb32 = (uint32_t)(32 * ldo);
+            mbar_arrive_expect_tx(&tail->gt_full[gbuf], 2u * nt * rb32);
+            bulk_g2s(gdst, gsrc + (long)g.p0 * ldo, rb32, &tail->gt_full[gbuf]);
+            bulk_g2s(gdst + rb32, gsrc + (long)g.p1 * ldo, rb32, &tail->gt_full[gbuf]);
+            if (nt == 2) {
+              bulk_g2s(gdst + 16384, tsrc + (long)g.p0 * ldo, rb32, &tail->gt_full[gbuf]);
+              bulk_g2s(gdst + 16384 + rb32, tsrc + (long)g.p1 * ldo, rb32, &tail->gt_full[gbuf]);
+            }
+          } else {
+            const uint32_t gb = (uint32_t)(g.nv * ldo);
+            mbar_arrive_expect_tx(&tail->gt_full[gbuf], nt * gb);
+            bulk_g2s(gdst, gsrc + (long)g.p0 * ldo, gb, &tail->gt_full[gbuf]);
+            if (nt == 2) bulk_g2s(gdst + 16384, tsrc + (long)g.p0 * ldo, gb, &tail->gt_full[gbuf]);
+          }
+        }
+        // ---- the source pieces
+        const uint32_t b = (uint32_t)i & 1u;
+        mbar_wait(&tail->x_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        if (i < 12) CUNET_TRACE_MARK(trace, 1 + 2 * i);
+        uint32_t xtot = 0;
+        for (int s = 0; s < p.in.nseg; ++s) {
+          const cunet_seg& sg = p.in.seg[s];
+          xtot += (uint32_t)((sg.up ? g.nlow : g.nv) * sg.C * 2);
+        }
+        mbar_arrive_expect_tx(&tail->x_full[b], xtot);
+        uint8_t* xdst = smem + L.x_off + b * L.x_bytes;
+        for (int s = 0; s < p.in.nseg; ++s) {
+          const cunet_seg& sg = p.in.seg[s];
+          const char* src = reinterpret_cast<const char*>(sg.ptr);
+          const int Cp2 = sg.C * 2;
+          if (sg.up) {
+            bulk_g2s(xdst + tail->xoff[s], src + (long)g.low0 * Cp2, (uint32_t)(g.nlow * Cp2), &tail->x_full[b]);
+          } else if (split) {
+            bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
+            bulk_g2s(xdst + tail->xoff[s] + 32 * Cp2, src + (long)g.p1 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
+          } else {
+            bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(g.nv * Cp2), &tail->x_full[b]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================== G store issuer
+    if (lane == 0) {
+      for (int i = 0; i < ns; ++i) {
+        const F1Geo g = f1_geo(st0 + i, M, W, split, need_low);
+        const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
+        const uint8_t* xsrc = smem + L.x_off + b * L.x_bytes;
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(&tail->g_ready[b][c], upar);
+          for (int s = 0; s < p.in.nseg; ++s) {
+            if ((tail->seg_start[s] >> 7) != c || p.gacc[s].G == nullptr) continue;
+            const cunet_seg& sg = p.in.seg[s];
+            const int Cp2 = sg.C * 2;
+            char* G = reinterpret_cast<char*>(p.gacc[s].G);
+            const uint8_t* src = xsrc + tail->xoff[s];
+            const int acc = p.gacc[s].accumulate;
+            if (sg.up) {
+              if (acc) f1_bulk_red_add_bf16(G + (long)g.low0 * Cp2, src, (uint32_t)(g.nlow * Cp2));
+              else f1_bulk_s2g(G + (long)g.low0 * Cp2, src, (uint32_t)(g.nlow * Cp2));
+            } else if (split) {
+              if (acc) {
+                f1_bulk_red_add_bf16(G + (long)g.p0 * Cp2, src, (uint32_t)(32 * Cp2));
+                f1_bulk_red_add_bf16(G + (long)g.p1 * Cp2, src + 32 * Cp2, (uint32_t)(32 * Cp2));
+              } else {
+                f1_bulk_s2g(G + (long)g.p0 * Cp2, src, (uint32_t)(32 * Cp2));
+                f1_bulk_s2g(G + (long)g.p1 * Cp2, src + 32 * Cp2, (uint32_t)(32 * Cp2));
+              }
+            } else {
+              if (acc) f1_bulk_red_add_bf16(G + (long)g.p0 * Cp2, src, (uint32_t)(g.nv * Cp2));
+              else f1_bulk_s2g(G + (long)g.p0 * Cp2, src, (uint32_t)(g.nv * Cp2));
+            }
+          }
+          f1_bulk_commit();
+        }
+        f1_bulk_wait_read0();   // the x buffer may be overwritten once the stores have read it
+        if (i < 12) CUNET_TRACE_MARK(trace, 200 + 2 * i);
+        mbar_arrive(&tail->x_free[b]);
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================== dgrad MMA issuer: D1[(stage, chunk)] = W_c * dT^T
+    if (lane == 0 && ns > 0) {
+      const uint32_t idesc_d = make_idesc(Elem<bf16>::FMT, 128, 64, 0, 0);
+      const uint32_t wA = smem_u32(smem + L.w_off), dT = smem_u32(smem + L.dt_off);
+      mbar_wait(&tail->w_full, 0);
+      uint32_t it = 0;
+      for (int i = 0; i < ns; ++i) {
+        mbar_wait(&tail->dt_ready, (uint32_t)i & 1u);
+        if (i < 12) CUNET_TRACE_MARK(trace, 96 + 3 * i);
+        for (int c = 0; c < nchunk; ++c, ++it) {
+          const uint32_t buf = it & 1u;
+          const int rows = min(128, Cin - c * 128);
+          mbar_wait(&tail->d1_free[buf], ((it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d1 = tmem + 384u + buf * 64u;
+          const uint32_t wc = wA + (uint32_t)tail->woff[c];
+          for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma<bf16>(d1, make_sdesc(wc + kb * rows * 128 + kk * 32, 16, 1024),
+                         make_sdesc(dT + kb * F1_SUB + kk * 32, 16, 1024), idesc_d, (uint32_t)((kb | kk) != 0));
+          }
+          tc_commit(&tail->d1_full[buf]);
+          if (c == 0 && i < 12) CUNET_TRACE_MARK(trace, 97 + 3 * i);
+        }
+        tc_commit(&tail->dt_free);
+        if (i < 12) CUNET_TRACE_MARK(trace, 98 + 3 * i);
+      }
+    }
+  } else if (warp == 3) {
+    // ============================================================== wgrad MMA issuer: D2_c += A_c^T * dT
+    if (lane == 0 && ns > 0) {
+      const uint32_t idesc_w = make_idesc(Elem<bf16>::FMT, 128, (uint32_t)L.npad, 1, 1);  // both operands MN-major
+      const uint32_t dT = smem_u32(smem + L.dt_off), aA = smem_u32(smem + L.a_off);
+      uint32_t ai = 0;
+      for (int i = 0; i < ns; ++i) {
+        mbar_wait(&tail->dt_ready, (uint32_t)i & 1u);
+        for (int c = 0; c < nchunk; ++c, ++ai) {
+          const uint32_t slot = ai & 1u;
+          mbar_wait(&tail->a_full[slot], (ai >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t a = aA + slot * 16384u;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma<bf16>(tmem + (uint32_t)c * 128u, make_sdesc_mn<bf16>(a + kk * 2048, F1_SUB),
+                       make_sdesc_mn<bf16>(dT + kk * 2048, F1_SUB), idesc_w, (uint32_t)((i | kk) != 0));
+          tc_commit(&tail->a_free[slot]);
+        }
+        tc_commit(&tail->dt_free);
+      }
+      tc_commit(&tail->done);
+    }
+  } else if (is_tr) {
+    // ============================================================== transformers (256 threads)
+    const bool gcol_ok = cc * 8 < p.dy.C;
+    const bool gcol_used = cc * 8 < L.npad;
+    const uint32_t dtb = smem_u32(smem + L.dt_off), ab = smem_u32(smem + L.a_off);
+    const int* lowmap = tail->lowmap;
+    const int* rowpos = tail->rowpos;
+    GradCoef<bf16> gcf;
+    {
+      const int co2 = ((cc * 8) & 127) >> 1;
+      gcf.a = *reinterpret_cast<const uint4*>(&tail->ga2[co2]);
+      gcf.b = *reinterpret_cast<const uint4*>(&tail->gb2[co2]);
+      gcf.mu = *reinterpret_cast<const uint4*>(&tail->gmu2[co2]);
+      gcf.d = *reinterpret_cast<const uint4*>(&tail->gd2[co2]);
+    }
+    const int relu_on = p.in.bn_train == 2 ? 0 : 1;
+    uint32_t ai = 0;
+    for (int i = 0; i < ns; ++i) {
+      const int st = st0 + i;
+      const int nv = split ? F1_R : min(F1_R, M - st * F1_R);
+      const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
+      const int gbuf = L.gt_bufs == 2 ? (i & 1) : 0;
+      const uint32_t gu = (uint32_t)(L.gt_bufs == 2 ? (i >> 1) : i);
+      const uint32_t posadd = (!split && W == 64) ? (uint32_t)((st & 1) << 1) : 0u;   // image row parity (H even)
+      if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 32 + 4 * i);
+      mbar_wait(&tail->gt_full[gbuf], gu & 1u);
+      mbar_wait(&tail->dt_free, ((uint32_t)i & 1u) ^ 1u);   // MMAs of the previous stage no longer read the operand
+      if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 33 + 4 * i);
+      if (gcol_used) {
+        const uint32_t rg = smem_u32(smem + L.gt_off + gbuf * F1_GT_BYTES) + (uint32_t)cc * 16u;
+        const uint32_t ri = smem_u32(smem + L.gt_off + gbuf * F1_GT_BYTES + 24576) + (uint32_t)cc * 8u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = rb + 16 * q;
+          uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
+          if (gcol_ok && r < nv) {
+            GradRaw<bf16> raw;
+            const int loc = p.dy.pooled ? lowmap[r] : r;
+            raw.g = f1_lds128(rg + (uint32_t)(loc * ldo));
+            if (p.dy.mode == 1) raw.t = f1_lds128(rg + 16384u + (uint32_t)(loc * ldo));
+            if (p.dy.pooled) {
+              const uint2 iv = f1_lds64(ri + (uint32_t)(loc * p.dy.C));
+              raw.idx[0] = iv.x;
+              raw.idx[1] = iv.y;
+              raw.pos = (uint32_t)rowpos[r] + posadd;
+            }
+            o = gcf.apply(p.dy, raw, lo_unused);
+          }
+          sts128(dtb + (uint32_t)(cc >> 3) * F1_SUB + tile_off(r, cc & 7), o);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tail->dt_ready);
+        mbar_arrive(&tail->gt_free[gbuf]);
+      }
+      if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 34 + 4 * i);
+      // ---- activation operand per chunk -> A slots
+      mbar_wait(&tail->x_full[b], upar);
+      const uint32_t xb = smem_u32(smem + L.x_off + b * L.x_bytes);
+#pragma unroll
+      for (int c = 0; c < F1_MAXCH; ++c) {
+        if (c >= nchunk) break;
+        const uint32_t slot = ai & 1u;
+        ActCoef<bf16> acf;
+        acf.sc = *reinterpret_cast<const uint4*>(&tail->sc2[(c * 128 + cc * 8) >> 1]);
+        acf.sh = *reinterpret_cast<const uint4*>(&tail->sh2[(c * 128 + cc * 8) >> 1]);
+        acf.relu = relu_on;
+        mbar_wait(&tail->a_free[slot], ((ai >> 1) & 1u) ^ 1u);
+        const uint32_t abase = ab + slot * 16384u;
+        const int s = cs_s[c];
+        const uint32_t rx = xb + (uint32_t)(s < 0 ? 0 : tail->xoff[s]) + (uint32_t)cs_cl2[c];
+        const int ldx = cs_ldx[c];
+        uint4 raw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = rb + 16 * q;
+          raw[q] = make_uint4(0, 0, 0, 0);
+          if (s >= 0 && r < nv) raw[q] = f1_lds128(rx + (uint32_t)((cs_up[c] ? lowmap[r] : r) * ldx));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = rb + 16 * q;
+          uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
+          if (s >= 0 && r < nv) o = acf.apply(raw[q], lo_unused);
+          sts128(abase + (uint32_t)(cc >> 3) * F1_SUB + tile_off(r, cc & 7), o);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tail->a_full[slot]);
+          mbar_arrive(&tail->a_done[b][c]);   // the epilogue may now overwrite this chunk's x with gamma*dz
+        }
+        ++ai;
+      }
+      if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 35 + 4 * i);
+    }
+  } else if (is_ep) {
+    // ============================================================== epilogue (512 threads)
+    float a_db[F1_MAXCH], a_dg[F1_MAXCH];
+#pragma unroll
+    for (int c = 0; c < F1_MAXCH; ++c) a_db[c] = a_dg[c] = 0.f;
+    // upsampled source: the two 8-column TMEM windows that hold the 16 children of this thread's 4 low pixels
+    uint32_t upA = 0, upB = 0;
+    if (W >= 32) {                 // split, or two whole rows of 32: rows 2j.. of both image rows
+      upA = (uint32_t)(8 * pq);
+      upB = (uint32_t)(32 + 8 * pq);
+    } else if (W == 16) {
+      upA = (uint32_t)(32 * (pq >> 1) + 8 * (pq & 1));
+      upB = upA + 16u;
+    } else {                       // W == 8: two rows of 8; W == 4: four rows of 4
+      upA = (uint32_t)(16 * pq);
+      upB = upA + 8u;
+    }
+    uint32_t it = 0;
+    for (int i = 0; i < ns; ++i) {
+      const int nv = split ? F1_R : min(F1_R, M - (st0 + i) * F1_R);
+      const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
+      const uint32_t xb = smem_u32(smem + L.x_off + b * L.x_bytes);
+#pragma unroll
+      for (int c = 0; c < F1_MAXCH; ++c) {
+        if (c >= nchunk) break;
+        const uint32_t buf = it & 1u;
+        mbar_wait(&tail->d1_full[buf], (it >> 1) & 1u);
+        mbar_wait(&tail->x_full[b], upar);        // completed long ago: acquires the landed x for this thread
+        mbar_wait(&tail->a_done[b][c], upar);     // the transformers have read this chunk's x
+        if (tid == 384 && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 144 + 4 * i);
+        tc_fence_after();
+        const int ps = e_ps[c];
+        if (ps >= 0) {
+          const cunet_seg& sg = p.in.seg[ps];
+          const uint32_t Cp2 = (uint32_t)sg.C * 2u;
+          const uint32_t xa = xb + (uint32_t)tail->xoff[ps] + (uint32_t)((c * 128 + k - tail->seg_start[ps]) * 2);
+          const float sc = e_sc[c], sh = e_sh[c], is = e_is[c], nmi = e_nmi[c], gm = e_gm[c];
+          const uint32_t tb = tmem + 384u + buf * 64u + ((uint32_t)(qd * 32) << 16);
+          float db0 = 0.f, db1 = 0.f, dg0 = 0.f, dg1 = 0.f;
+          float v[16];
+          if (!sg.up) {
+            // this thread's 16 pixels: stage rows 16 pq .. 16 pq + 15
+            const int r0 = 16 * pq;
+            const int nvl = nv - r0;
+            if (nvl > 0) {
+              f1_tmem_ld16_nowait(tb + (uint32_t)r0, v);
+              const uint32_t a0 = xa + (uint32_t)r0 * Cp2;
+              float x[16];
+              if (nvl >= 16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) x[q] = f1_lds_bf16(a0 + (uint32_t)q * Cp2);
+                f1_tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 16; q += 2) {
+                  const float dz0 = fmaf(x[q], sc, sh) > 0.f ? v[q] : 0.f;
+                  const float dz1 = fmaf(x[q + 1], sc, sh) > 0.f ? v[q + 1] : 0.f;
+                  db0 += dz0;
+                  db1 += dz1;
+                  dg0 = fmaf(dz0, fmaf(x[q], is, nmi), dg0);
+                  dg1 = fmaf(dz1, fmaf(x[q + 1], is, nmi), dg1);
+                  v[q] = gm * dz0;
+                  v[q + 1] = gm * dz1;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                  f1_sts_u16(a0 + (uint32_t)q * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(v[q])));
+              } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) x[q] = q < nvl ? f1_lds_bf16(a0 + (uint32_t)q * Cp2) : 0.f;
+                f1_tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const float dz = (q < nvl && fmaf(x[q], sc, sh) > 0.f) ? v[q] : 0.f;
+                  db0 += dz;
+                  dg0 = fmaf(dz, fmaf(x[q], is, nmi), dg0);
+                  if (q < nvl) f1_sts_u16(a0 + (uint32_t)q * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz)));
+                }
+              }
+            }
+          } else {
+            // upsampled source: this thread's 4 half-resolution pixels (rows 4 pq .. 4 pq + 3 of the stage's low run)
+            // and their 16 children, gathered as a 2 x 8 image (W == 4: a 4 x 4 image)
+            const int nlow = split ? 16 : (nv >> 2);
+            const int l0 = 4 * pq;
+            if (l0 < nlow) {
+              f1_tmem_ld8_nowait(tb + upA, v);
+              f1_tmem_ld8_nowait(tb + upB, v + 8);
+              const uint32_t a0 = xa + (uint32_t)l0 * Cp2;
+              float x[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[j] = (l0 + j < nlow) ? f1_lds_bf16(a0 + (uint32_t)j * Cp2) : 0.f;
+              f1_tmem_wait_ld();
+              float d4[4];
+              if (W != 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d4[j] = (v[2 * j] + v[2 * j + 1]) + (v[8 + 2 * j] + v[9 + 2 * j]);
+              } else {
+                d4[0] = (v[0] + v[1]) + (v[4] + v[5]);
+                d4[1] = (v[2] + v[3]) + (v[6] + v[7]);
+                d4[2] = (v[8] + v[9]) + (v[12] + v[13]);
+                d4[3] = (v[10] + v[11]) + (v[14] + v[15]);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool ok = l0 + j < nlow;
+                const float dz = (ok && fmaf(x[j], sc, sh) > 0.f) ? d4[j] : 0.f;
+                db0 += dz;
+                dg0 = fmaf(dz, fmaf(x[j], is, nmi), dg0);
+                if (ok) f1_sts_u16(a0 + (uint32_t)j * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz)));
+              }
+            }
+          }
+          a_db[c] += db0 + db1;
+          a_dg[c] += dg0 + dg1;
+        }
+        fence_proxy_async();  // G written over x -> visible to the bulk store
+        tc_fence_before();
+        __syncwarp();
+        if (tid == 384 && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 145 + 4 * i);
+        if (lane == 0) {
+          mbar_arrive(&tail->g_ready[b][c]);
+          mbar_arrive(&tail->d1_free[buf]);
+        }
+        ++it;
+      }
+      if (tid == 384 && i < 12) CUNET_TRACE_MARK(trace, 146 + 4 * i);
+    }
+    if (ns > 0) {
+#pragma unroll
+      for (int c = 0; c < F1_MAXCH; ++c) {
+        const int ps = e_ps[c];
+        if (c >= nchunk || ps < 0) continue;
+        const int kg = c * 128 + k;
+        atomicAdd(p.dbeta + kg, a_db[c]);
+        atomicAdd(p.dgamma + kg, a_dg[c]);
+        if (p.gacc[ps].gstats) {
+          // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma)  (see conv_dgrad_v2.cu)
+          const int kl = kg - tail->seg_start[ps], Cp = p.in.seg[ps].C;
+          atomicAdd(p.gacc[ps].gstats + kl, (double)(e_gm[c] * a_db[c]));
+          atomicAdd(p.gacc[ps].gstats + Cp + kl, (double)(e_gm[c] * a_dg[c]));
+        }
+      }
+      // ---- weight gradient: D2_c[128 k][co] -> dW[co][k] (a warp adds 32 consecutive k of one co: coalesced)
+      mbar_wait(&tail->done, 0);
+      tc_fence_after();
+      if (tid == 384) CUNET_TRACE_MARK(trace, 230);
+      const int nq = L.npad >> 2;   // 16 or 32 output channels per pixel-quarter group of warps
+      for (int c = 0; c < nchunk; ++c) {
+        const int kg = c * 128 + k;
+        const bool kok = kg < Cin && kg < L.dwc;
+        for (int j = 0; j < nq; j += 16) {
+          float v[16];
+          const int col = pq * nq + j;
+          f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)(qd * 32) << 16) + (uint32_t)col, v);
+          f1_tmem_wait_ld();
+          if (kok) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (col + q < p.Cout) atomicAdd(L.dw + (long)(col + q) * L.dwc + kg, v[q]);
+          }
+        }
+      }
+      if (tid == 384) CUNET_TRACE_MARK(trace, 231);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace cunet
+using namespace cunet;
+
+CUNET_TRACE_SETTER(cunet_debug_trace_bwd1x1, g_f1_trace)
+
+// 1: handled by the fused kernel; 0: not eligible (caller runs the two separate kernels); <0: error
+static int conv_bwd1x1_try(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, cudaStream_t st) {
+  static const bool off = getenv("CUNET_BWD1X1_OFF") != nullptr;
+  if (off) return 0;
+  if (d->dtype != CUNET_BF16 || w->dtype != CUNET_BF16 || d->taps != 1 || w->taps != 1) return 0;
+  if (d->in.bn_train != 1) return 0;
+  if (d->dy.ld != d->dy.C || d->dy.C > 128 || (d->dy.C & 7) || d->CoutPad > 128 || d->CoutPad != d->dy.C) return 0;
+  if (w->Cout > 128 || w->Cout != d->Cout) return 0;
+  // same op on both sides
+  if (w->in.nseg != d->in.nseg || w->dy.g != d->dy.g || w->dy.t != d->dy.t || w->N != d->N || w->H != d->H ||
+      w->W != d->W || w->dy.mode != d->dy.mode || w->dy.pooled != d->dy.pooled)
+    return 0;
+  int cin = 0, up = 0, xbytes = 0;
+  const int W = d->W, H = d->H;
+  const int split_geo = (W == 64);
+  for (int s = 0; s < d->in.nseg; ++s) {
+    const cunet_seg& sg = d->in.seg[s];
+    if (sg.ld != sg.C || (sg.C != 32 && sg.C != 64 && sg.C != 128)) return 0;
+    if ((cin >> 7) != ((cin + sg.C - 1) >> 7)) return 0;   // a segment must not straddle a 128-channel chunk
+    if (w->in.seg[s].ptr != sg.ptr || w->in.seg[s].up != sg.up) return 0;
+    if (d->gacc[s].G && d->gacc[s].ld != sg.C) return 0;
+    cin += sg.C;
+    up |= sg.up;
+  }
+  if (cin > MAX_CIN || cin > 128 * F1_MAXCH) return 0;
+  if ((W & (W - 1)) || (H & (H - 1)) || W > 64 || W < 4 || H < 4) return 0;
+  if (up && d->dy.pooled) return 0;
+  const int split = (up && split_geo) ? 1 : 0;
+  const long M = (long)d->N * H * W;
+  if (M <= 0) return 1;
+  if (M > (1L << 30)) return 0;
+  if ((up || d->dy.pooled) && (M % 64) && ((M % 64) % (2 * W))) return 0;
+  if (w->dw_cin != 0 && w->dw_cin < cin) return 0;
+  // piece sizes inside an x buffer (must match the kernel's xoff table): 64 rows, or the <= 16 low rows of an
+  // upsampled source
+  for (int s = 0; s < d->in.nseg; ++s) xbytes += (d->in.seg[s].up ? 16 : F1_R) * d->in.seg[s].C * 2;
+  const int nkb = (d->CoutPad + 63) / 64;
+  F1Layout L;
+  L.w_off = 0;
+  const int wbytes = cin * 128 * nkb;
+  // the last chunk's weight rows are read as a full 128-row operand: keep 16 KB of readable slack behind them
+  L.dt_off = (wbytes + 1023) & ~1023;
+  L.a_off = L.dt_off + 2 * F1_SUB;
+  L.gt_off = L.a_off + 2 * 16384;
+  L.x_bytes = (xbytes + 1023) & ~1023;
+  if (L.x_bytes < 16384) L.x_bytes = 16384;   // the coefficient tables live there during the prologue
+  const int limit = 232448 - 1024 - (int)sizeof(F1Tail);
+  L.gt_bufs = (L.gt_off + 2 * F1_GT_BYTES + 2 * L.x_bytes <= limit) ? 2 : 1;
+  L.x_off = L.gt_off + L.gt_bufs * F1_GT_BYTES;
+  L.tail_off = L.x_off + 2 * L.x_bytes;
+  if (L.tail_off > limit) return 0;
+  L.split = split;
+  L.npad = ((d->dy.C + 63) / 64) * 64;
+  L.dwc = w->dw_cin > 0 ? w->dw_cin : cin;
+  L.dw = w->dw;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int total = (int)((M + F1_R - 1) / F1_R);
+  L.per = (total + sms - 1) / sms;
+  const int grid = (total + L.per - 1) / L.per;
+  const size_t smem = (size_t)L.tail_off + sizeof(F1Tail) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv_bwd1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_bwd1x1 attr", e);
+  e = cunet_launch(conv_bwd1x1_kernel, dim3(grid), dim3(F1_THREADS), smem, st, *d, L);
+  if (e != cudaSuccess) return cunet_fail_cuda("conv_bwd1x1 launch", e);
+  return 1;
+}
+
+extern "C" int cunet_conv_bwd1x1(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, void* stream) {
+  if (!d || !w) return cunet_fail("conv_bwd1x1: null params");
+  const int r = conv_bwd1x1_try(d, w, reinterpret_cast<cudaStream_t>(stream));
+  if (r != 0) return r < 0 ? r : 0;
+  const int rc = cunet_conv_dgrad(d, stream);
+  if (rc != 0) return rc;
+  return cunet_conv_wgrad(w, stream);
+}

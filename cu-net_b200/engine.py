@@ -52,6 +52,12 @@ class Engine(object):
         self.tdtype = torch.bfloat16 if self.dtype == L.BF16 else torch.float32
         self.double_bn_update = double_bn_update
         self.grad_scale = 1.0          # 1 / world_size under data parallelism
+        # pixel rows from which a 1x1 conv's backward runs as ONE fused dgrad+wgrad launch (CUNET_BWD1X1_MIN_ROWS)
+        import os
+        self.fuse1x1_min_rows = int(os.environ.get("CUNET_BWD1X1_MIN_ROWS", "12288"))
+        if os.environ.get("CUNET_BWD1X1_OFF"):
+            self.fuse1x1_min_rows = 1 << 62
+        self.wgrad_serial = os.environ.get("CUNET_WGRAD_SIDE", "1") == "0"   # debug: no side stream
         dev = self.device
         p = plan
 
@@ -158,6 +164,10 @@ class Engine(object):
 
     def _gstats(self, tname):
         return self.zbuf.data_ptr() + 8 * self.gstat_off[tname]
+
+    def is_fused_1x1(self, op):
+        """True when the backward of this op is the single fused dgrad+wgrad launch of csrc/conv_bwd1x1.cu."""
+        return op.taps == 1 and self.dtype == L.BF16 and self.N * op.res * op.res >= self.fuse1x1_min_rows
 
     def _concat(self, cc, op, mode):
         """mode: 1 train, 0 eval."""
@@ -302,6 +312,11 @@ class Engine(object):
                 # dense-layer 3x3: backward-data and backward-filter share the im2col of the output gradient ->
                 # one fused launch on the main stream (csrc/conv_bwd3x3.cu)
                 calls.append((lib.cunet_conv_bwd3x3, (dp, wp)))
+            elif self.is_fused_1x1(op):
+                # large 1x1: backward-data and backward-filter share the gradient operand and the landed sources ->
+                # one fused launch (csrc/conv_bwd1x1.cu).  Small maps stay split: there a launch is pure latency and
+                # the backward-filter hides on the side stream behind the backward-data chain.
+                calls.append((lib.cunet_conv_bwd1x1, (dp, wp)))
             else:
                 calls.append((lib.cunet_conv_dgrad, dp))
                 wcalls.append((len(calls) - 1, lib.cunet_conv_wgrad, wp))  # may start once dgrad #k may start
@@ -389,7 +404,7 @@ class Engine(object):
         main = torch.cuda.current_stream()
         side = self.side_stream
         probes = getattr(self, "probes", None)
-        if probes:                      # instrumentation mode (bench probes): plain serial order
+        if probes or self.wgrad_serial:  # instrumentation mode (bench probes) / CUNET_WGRAD_SIDE=0: plain serial order
             k = 0
             for i, (fn, prm) in enumerate(self.bwd_calls):
                 self._run([(fn, prm)])
@@ -552,7 +567,11 @@ class Trainer(object):
             self.eng.optimizer_step(self.alpha, self.eps)
 
     def _capture(self):
-        # warm-up on a side stream (sets kernel attributes, allocates nothing afterwards), then capture
+        # warm-up on a side stream (sets kernel attributes, allocates nothing afterwards), then capture.  The warm-up
+        # is a real step on whatever sits in the input buffers: the model state it touches (parameters, optimizer
+        # state, BatchNorm running statistics and counters) is put back, so capturing is invisible to training
+        e = self.eng
+        keep = [t.clone() for t in (e.params, e.sq_avg, e.bnbuf, e.counters)]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -560,6 +579,9 @@ class Trainer(object):
             self._opt()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        for t, k in zip((e.params, e.sq_avg, e.bnbuf, e.counters), keep):
+            t.copy_(k)
+        del keep
         self._g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g_fb):
             self._fwd_bwd()

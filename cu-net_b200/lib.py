@@ -120,7 +120,7 @@ def load():
 # every symbol include/cunet_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "cunet_last_error", "cunet_abi_version",
-    "cunet_conv_fwd", "cunet_debug_fwd_v2_min_tiles", "cunet_conv_dgrad", "cunet_debug_dgrad_trace", "cunet_conv_wgrad", "cunet_conv_bwd3x3", "cunet_pack_weights", "cunet_pack_fwd_bytes",
+    "cunet_conv_fwd", "cunet_debug_fwd_v2_min_tiles", "cunet_conv_dgrad", "cunet_debug_dgrad_trace", "cunet_conv_wgrad", "cunet_conv_bwd3x3", "cunet_conv_bwd1x1", "cunet_pack_weights", "cunet_pack_fwd_bytes",
     "cunet_pack_dgrad_bytes", "cunet_stem_im2col", "cunet_stem_pool_fwd", "cunet_stem_bwd", "cunet_mse_decode",
     "cunet_decode_finalize", "cunet_bn_running_update", "cunet_rmsprop_step",
     "cunet_quant_forward", "cunet_quant_restore", "cunet_quant_grad", "cunet_quant_input_fwd",
@@ -164,6 +164,10 @@ def conv_wgrad(params):
 
 def conv_bwd3x3(dparams, wparams):
     check(load().cunet_conv_bwd3x3(C.byref(dparams), C.byref(wparams), stream_ptr()), "cunet_conv_bwd3x3")
+
+
+def conv_bwd1x1(dparams, wparams):
+    check(load().cunet_conv_bwd1x1(C.byref(dparams), C.byref(wparams), stream_ptr()), "cunet_conv_bwd1x1")
 
 
 def pack_weights(descs_dev_ptr, ndesc, dtype):

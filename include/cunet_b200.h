@@ -155,6 +155,14 @@ int cunet_debug_fwd_v2_min_tiles(int min_tiles);
  * other configuration falls back to the two calls above, in that order, on `stream`. */
 int cunet_conv_bwd3x3(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, void* stream);
 
+/* Fused backward of a 1x1 fused conv -- adapters (models/cu_net.py:19-35), dense-layer conv1 (:41-44, 52-61),
+ * intermedia adapters (:147-190), heat-map heads (:192-198): exactly cunet_conv_dgrad(d) followed by
+ * cunet_conv_wgrad(w) for the SAME op (same `in`, same `dy`), in one launch that lands every operand once
+ * (csrc/conv_bwd1x1.cu).  bf16, taps == 1, Cin <= 384 in 32/64/128-channel segments, power-of-two H, W in [4, 64]
+ * run in the fused persistent kernel; every other configuration falls back to the two calls above, in that
+ * order, on `stream`. */
+int cunet_conv_bwd1x1(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_params* w, void* stream);
+
 /* ---- stem: conv0 7x7 s2 p3 -> norm0 -> relu0 -> pool0 (models/cu_net.py:299-304) ------------------
  * conv0 runs on the tensor cores through cunet_conv_fwd / cunet_conv_wgrad with an identity input
  * (bn_train == 2) over an im2col matrix [N*Ho*Wo][160] (147 = 3*7*7 columns in the reference's

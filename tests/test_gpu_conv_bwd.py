@@ -243,3 +243,74 @@ def test_conv_bwd3x3_fused(case):
     assert _relerr(dgamma, dg_ref) < tol, "dgamma %g" % _relerr(dgamma, dg_ref)
     errw = _relerr(dw.reshape(cout, 128, -1), dw_ref.reshape(cout, 128, -1))
     assert errw < 2e-2, "%s dW rel err %g" % (name, errw)
+
+
+F1_CASES = [c for c in CASES if c[7] == 1]      # every 1x1 case (the fused kernel falls back when not eligible)
+
+
+@pytest.mark.parametrize("case", F1_CASES, ids=[c[0] for c in F1_CASES])
+def test_conv_bwd1x1_fused(case):
+    """cunet_conv_bwd1x1 (one fused launch, csrc/conv_bwd1x1.cu) == dgrad + wgrad of the 1x1 fused conv, bf16: source
+    gradients (write and accumulate segments), their statistics shares, dgamma / dbeta and dW, at every shape of the
+    network incl. the bench shapes (upsampled source at 64x64 = split stage geometry, pooled output, heads)."""
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.BF16
+    name, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad = case
+    cs = make_case(lib, dtype, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad, seed=7)
+    dev, td, cin = cs["dev"], cs["td"], cs["cin"]
+    nbytes = lib.pack_dgrad_bytes(cin, taps, cs["cout_pad"], dtype)
+    wpack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    desc = lib.PackDesc(cs["weight"].data_ptr(), None, wpack.data_ptr(), cout, cin, taps, cs["cout_pad"])
+    desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).to(dev)
+    lib.pack_weights(desc_dev.data_ptr(), 1, dtype)
+
+    dp = lib.ConvDgradParams()
+    fill_concat(dp.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"],
+                cs["gamma"], True)
+    fill_grad_src(dp.dy, cs, dy_mode)
+    gen = torch.Generator(device="cpu").manual_seed(99)
+    Gs, G0, gst = [], [], []
+    for i, x in enumerate(cs["srcs"]):
+        accumulate = i % 2
+        g0 = (torch.randn(x.shape, generator=gen) * 0.05).to(dev).to(td) if accumulate else \
+            torch.full(x.shape, float("nan"), device=dev, dtype=td)
+        G0.append(g0.clone())
+        Gs.append(g0)
+        st = torch.zeros(2 * x.shape[1], dtype=torch.float64, device=dev)
+        gst.append(st)
+        dp.gacc[i].G, dp.gacc[i].gstats, dp.gacc[i].ld, dp.gacc[i].accumulate = g0.data_ptr(), st.data_ptr(), x.shape[1], accumulate
+    dgamma = torch.zeros(cin, device=dev)
+    dbeta = torch.zeros(cin, device=dev)
+    dp.N, dp.H, dp.W, dp.taps = n, h, w, taps
+    dp.wpack_dgrad, dp.Cout, dp.CoutPad = wpack.data_ptr(), cout, cs["cout_pad"]
+    dp.dgamma, dp.dbeta, dp.dtype = dgamma.data_ptr(), dbeta.data_ptr(), dtype
+
+    dw = torch.zeros(cout, cin, taps, device=dev)
+    wp = lib.ConvWgradParams()
+    fill_concat(wp.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"],
+                cs["gamma"], True)
+    fill_grad_src(wp.dy, cs, dy_mode)
+    wp.N, wp.H, wp.W, wp.taps, wp.Cout = n, h, w, taps, cout
+    wp.dw, wp.nsplit, wp.dtype = dw.data_ptr(), 0, dtype
+
+    xs_before = [x.clone() for x in cs["srcs"]]
+    lib.conv_bwd1x1(dp, wp)
+    torch.cuda.synchronize()
+    for x, x0 in zip(cs["srcs"], xs_before):
+        assert torch.equal(x, x0), "the kernel must not modify its inputs"
+
+    outs, dg_ref, db_ref, dw_ref = reference(cs, n, h, w, ups, dy_mode)
+    tol = 2.5e-2
+    for i, (G, ref) in enumerate(zip(Gs, outs)):
+        exp = ref + (G0[i].float() if i % 2 else 0)
+        assert torch.isfinite(G.float()).all(), "segment %d has unwritten rows" % i
+        err = _relerr(G.float(), exp)
+        assert err < tol, "%s G[%d] rel err %g" % (name, i, err)
+        st_ref = ops_ref.gstats_of(ref, cs["srcs"][i], cs["stats"][i], cs["counts"][i])
+        c = G.shape[1]
+        assert _relerr(gst[i][:c], st_ref[:c]) < tol and _relerr(gst[i][c:], st_ref[c:]) < tol, "gstats %d" % i
+    assert _relerr(dbeta, db_ref) < tol, "dbeta %g" % _relerr(dbeta, db_ref)
+    assert _relerr(dgamma, dg_ref) < tol, "dgamma %g" % _relerr(dgamma, dg_ref)
+    errw = _relerr(dw.reshape(cout, cin, -1), dw_ref.reshape(cout, cin, -1))
+    assert errw < 2e-2, "%s dW rel err %g" % (name, errw)
