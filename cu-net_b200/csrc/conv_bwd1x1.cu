@@ -58,7 +58,7 @@ struct F1Tail {
   alignas(16) uint32_t sh2[MAX_CIN / 2];
   alignas(16) uint32_t ga2[64], gb2[64], gmu2[64], gd2[64];   // bf16x2 gradient-form coefficients (GradSmem packed)
   uint64_t w_full, dt_ready, dt_free, done;
-  uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[2], d1_free[2], a_full[2], a_free[2];
+  uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[4], d1_free[4], a_full[2], a_free[2];
   uint64_t a_done[2][F1_MAXCH], g_ready[2][F1_MAXCH];
   uint32_t tmem_base;
   int seg_start[CUNET_MAX_SEG + 1];
@@ -88,6 +88,47 @@ __device__ __forceinline__ float f1_lds_bf16(uint32_t saddr) {
 __device__ __forceinline__ void f1_sts_u16(uint32_t saddr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
 }
+// same with a compile-time byte offset folded into the instruction (no address arithmetic per access)
+template <int OFF> __device__ __forceinline__ float f1_lds_bf16_o(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(saddr), "n"(OFF));
+  return __uint_as_float((uint32_t)v << 16);
+}
+template <int OFF> __device__ __forceinline__ void f1_sts_u16_o(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(saddr), "n"(OFF), "h"(v) : "memory");
+}
+// 4 consecutive fp32 added to global memory with one reduction (sm_90+)
+__device__ __forceinline__ void f1_red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 16 pixels of one channel (the thread's TMEM lane): dz = dA * [x on the active side of the ReLU threshold],
+// accumulates sum dz and sum dz*x, overwrites x in place with gamma*dz.  CP2 = bytes between consecutive pixels.
+template <int CP2>
+__device__ __forceinline__ void f1_ep16(uint32_t a0, float* v, float thr, bool neg, float gm, float& db0, float& db1,
+                                        float& dx0, float& dx1) {
+  float x[16];
+#define F1_LD(q) x[q] = f1_lds_bf16_o<(q) * CP2>(a0);
+  F1_LD(0) F1_LD(1) F1_LD(2) F1_LD(3) F1_LD(4) F1_LD(5) F1_LD(6) F1_LD(7)
+  F1_LD(8) F1_LD(9) F1_LD(10) F1_LD(11) F1_LD(12) F1_LD(13) F1_LD(14) F1_LD(15)
+#undef F1_LD
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < 16; q += 2) {
+    const float dz0 = ((x[q] > thr) != neg) ? v[q] : 0.f;
+    const float dz1 = ((x[q + 1] > thr) != neg) ? v[q + 1] : 0.f;
+    db0 += dz0;
+    db1 += dz1;
+    dx0 = fmaf(dz0, x[q], dx0);
+    dx1 = fmaf(dz1, x[q + 1], dx1);
+    v[q] = gm * dz0;
+    v[q + 1] = gm * dz1;
+  }
+#define F1_ST(q) f1_sts_u16_o<(q) * CP2>(a0, __bfloat16_as_ushort(__float2bfloat16_rn(v[q])));
+  F1_ST(0) F1_ST(1) F1_ST(2) F1_ST(3) F1_ST(4) F1_ST(5) F1_ST(6) F1_ST(7)
+  F1_ST(8) F1_ST(9) F1_ST(10) F1_ST(11) F1_ST(12) F1_ST(13) F1_ST(14) F1_ST(15)
+#undef F1_ST
+}
+
 __device__ __forceinline__ uint4 f1_lds128(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
@@ -101,22 +142,16 @@ __device__ __forceinline__ uint2 f1_lds64(uint32_t saddr) {
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread; the wait is separate so that two loads can be
 // in flight before the first use
 __device__ __forceinline__ void f1_tmem_ld16_nowait(uint32_t taddr, float* v) {
-  uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void f1_tmem_ld8_nowait(uint32_t taddr, float* v) {
-  uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void f1_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void f1_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -176,6 +211,11 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
   const int ns = max(0, st1 - st0);
   const int ldo = p.dy.ld * 2;
   const int split = L.split;
+  // TMEM: wgrad accumulators D2_c at columns c*128 (the last chunk only as wide as its real channels), then a ring of
+  // 64-column dgrad accumulators D1 in what is left (2 buffers for 384 input channels, 3 for 320, 4 below)
+  const int d2cols = ((Cin + 63) >> 6) << 6;
+  const uint32_t d1_base = (uint32_t)d2cols;
+  const uint32_t d1_nbuf = (uint32_t)min(4, (512 - d2cols) >> 6);
   int need_low = p.dy.pooled;
   for (int s = 0; s < p.in.nseg; ++s) need_low |= p.in.seg[s].up;
   CUNET_TRACE_LOAD(trace, g_f1_trace)
@@ -192,6 +232,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       mbar_init(&tail->x_free[b], 1);
       mbar_init(&tail->d1_full[b], 1);
       mbar_init(&tail->d1_free[b], 16);
+      mbar_init(&tail->d1_full[b + 2], 1);
+      mbar_init(&tail->d1_free[b + 2], 16);
       mbar_init(&tail->a_full[b], 8);
       mbar_init(&tail->a_free[b], 1);
       for (int c = 0; c < F1_MAXCH; ++c) {
@@ -256,12 +298,15 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
   // transformer constants (coefficients stay in shared memory: tail->sc2 / sh2 / ga2 ...)
   int cs_s[F1_MAXCH], cs_cl2[F1_MAXCH], cs_ldx[F1_MAXCH], cs_up[F1_MAXCH];
   // epilogue constants
-  float e_sc[F1_MAXCH], e_sh[F1_MAXCH], e_is[F1_MAXCH], e_nmi[F1_MAXCH], e_gm[F1_MAXCH];
+  // ReLU mask of channel k: bn(x) = sc*x + sh > 0  <=>  (x > thr) != neg  with thr = -sh/sc, neg = sc < 0
+  float e_thr[F1_MAXCH], e_is[F1_MAXCH], e_nmi[F1_MAXCH], e_gm[F1_MAXCH];
+  bool e_neg[F1_MAXCH];
   int e_ps[F1_MAXCH];
 #pragma unroll
   for (int c = 0; c < F1_MAXCH; ++c) {
     cs_s[c] = -1; cs_cl2[c] = 0; cs_ldx[c] = 0; cs_up[c] = 0;
-    e_sc[c] = e_sh[c] = e_is[c] = e_nmi[c] = e_gm[c] = 0.f;
+    e_thr[c] = e_is[c] = e_nmi[c] = e_gm[c] = 0.f;
+    e_neg[c] = false;
     e_ps[c] = -1;
   }
   // packed coefficient tables -> tail (they outlive the prologue area)
@@ -297,8 +342,10 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         int s = 0;
         while (kg >= tail->seg_start[s + 1]) ++s;
         e_ps[c] = s;
-        e_sc[c] = bn->scale[kg];
-        e_sh[c] = bn->shift[kg];
+        const float sc = bn->scale[kg], sh = bn->shift[kg];
+        const float inf = __int_as_float(0x7f800000);
+        e_neg[c] = sc < 0.f;
+        e_thr[c] = sc != 0.f ? -sh / sc : (sh > 0.f ? -inf : inf);   // sc == 0: the mask is the sign of the shift
         e_is[c] = bn->istd[kg];
         e_nmi[c] = -bn->mean[kg] * bn->istd[kg];  // xhat = x * istd - mean * istd
         e_gm[c] = p.in.gamma[kg];
@@ -426,16 +473,15 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       const uint32_t idesc_d = make_idesc(Elem<bf16>::FMT, 128, 64, 0, 0);
       const uint32_t wA = smem_u32(smem + L.w_off), dT = smem_u32(smem + L.dt_off);
       mbar_wait(&tail->w_full, 0);
-      uint32_t it = 0;
+      uint32_t buf = 0, bph = 0;     // ring position of the next D1 accumulator and its use parity
       for (int i = 0; i < ns; ++i) {
         mbar_wait(&tail->dt_ready, (uint32_t)i & 1u);
         if (i < 12) CUNET_TRACE_MARK(trace, 96 + 3 * i);
-        for (int c = 0; c < nchunk; ++c, ++it) {
-          const uint32_t buf = it & 1u;
+        for (int c = 0; c < nchunk; ++c) {
           const int rows = min(128, Cin - c * 128);
-          mbar_wait(&tail->d1_free[buf], ((it >> 1) & 1u) ^ 1u);
+          mbar_wait(&tail->d1_free[buf], bph ^ 1u);
           tc_fence_after();
-          const uint32_t d1 = tmem + 384u + buf * 64u;
+          const uint32_t d1 = tmem + d1_base + buf * 64u;
           const uint32_t wc = wA + (uint32_t)tail->woff[c];
           for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
@@ -445,15 +491,20 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           }
           tc_commit(&tail->d1_full[buf]);
           if (c == 0 && i < 12) CUNET_TRACE_MARK(trace, 97 + 3 * i);
+          if (++buf == d1_nbuf) {
+            buf = 0;
+            bph ^= 1u;
+          }
         }
         tc_commit(&tail->dt_free);
         if (i < 12) CUNET_TRACE_MARK(trace, 98 + 3 * i);
       }
     }
   } else if (warp == 3) {
-    // ============================================================== wgrad MMA issuer: D2_c += A_c^T * dT
+    // ============================================================== wgrad MMA issuer: D2_c[co][k] += dT^T * A_c
+    // (output channel = TMEM lane, input channel = column: a thread of the final epilogue then holds consecutive k of
+    //  one co, i.e. consecutive floats of dW[co][:], and adds them with 16-byte reductions)
     if (lane == 0 && ns > 0) {
-      const uint32_t idesc_w = make_idesc(Elem<bf16>::FMT, 128, (uint32_t)L.npad, 1, 1);  // both operands MN-major
       const uint32_t dT = smem_u32(smem + L.dt_off), aA = smem_u32(smem + L.a_off);
       uint32_t ai = 0;
       for (int i = 0; i < ns; ++i) {
@@ -463,10 +514,11 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           mbar_wait(&tail->a_full[slot], (ai >> 1) & 1u);
           tc_fence_after();
           const uint32_t a = aA + slot * 16384u;
+          const uint32_t idesc_w = make_idesc(Elem<bf16>::FMT, 128, (uint32_t)min(128, Cin - c * 128), 1, 1);  // MN-major both
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma<bf16>(tmem + (uint32_t)c * 128u, make_sdesc_mn<bf16>(a + kk * 2048, F1_SUB),
-                       make_sdesc_mn<bf16>(dT + kk * 2048, F1_SUB), idesc_w, (uint32_t)((i | kk) != 0));
+            umma<bf16>(tmem + (uint32_t)c * 128u, make_sdesc_mn<bf16>(dT + kk * 2048, F1_SUB),
+                       make_sdesc_mn<bf16>(a + kk * 2048, F1_SUB), idesc_w, (uint32_t)((i | kk) != 0));
           tc_commit(&tail->a_free[slot]);
         }
         tc_commit(&tail->dt_free);
@@ -588,7 +640,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       upA = (uint32_t)(16 * pq);
       upB = upA + 8u;
     }
-    uint32_t it = 0;
+    uint32_t buf = 0, bph = 0;       // ring position of the next D1 accumulator and its use parity
     for (int i = 0; i < ns; ++i) {
       const int nv = split ? F1_R : min(F1_R, M - (st0 + i) * F1_R);
       const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
@@ -596,8 +648,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
 #pragma unroll
       for (int c = 0; c < F1_MAXCH; ++c) {
         if (c >= nchunk) break;
-        const uint32_t buf = it & 1u;
-        mbar_wait(&tail->d1_full[buf], (it >> 1) & 1u);
+        mbar_wait(&tail->d1_full[buf], bph);
         mbar_wait(&tail->x_full[b], upar);        // completed long ago: acquires the landed x for this thread
         mbar_wait(&tail->a_done[b][c], upar);     // the transformers have read this chunk's x
         if (tid == 384 && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 144 + 4 * i);
@@ -607,9 +658,10 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           const cunet_seg& sg = p.in.seg[ps];
           const uint32_t Cp2 = (uint32_t)sg.C * 2u;
           const uint32_t xa = xb + (uint32_t)tail->xoff[ps] + (uint32_t)((c * 128 + k - tail->seg_start[ps]) * 2);
-          const float sc = e_sc[c], sh = e_sh[c], is = e_is[c], nmi = e_nmi[c], gm = e_gm[c];
-          const uint32_t tb = tmem + 384u + buf * 64u + ((uint32_t)(qd * 32) << 16);
-          float db0 = 0.f, db1 = 0.f, dg0 = 0.f, dg1 = 0.f;
+          const float thr = e_thr[c], gm = e_gm[c];
+          const bool neg = e_neg[c];
+          const uint32_t tb = tmem + d1_base + buf * 64u + ((uint32_t)(qd * 32) << 16);
+          float db0 = 0.f, db1 = 0.f, dx0 = 0.f, dx1 = 0.f;   // sum dz, sum dz*x (xhat applied once at the end)
           float v[16];
           if (!sg.up) {
             // this thread's 16 pixels: stage rows 16 pq .. 16 pq + 15
@@ -618,34 +670,20 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
             if (nvl > 0) {
               f1_tmem_ld16_nowait(tb + (uint32_t)r0, v);
               const uint32_t a0 = xa + (uint32_t)r0 * Cp2;
-              float x[16];
               if (nvl >= 16) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) x[q] = f1_lds_bf16(a0 + (uint32_t)q * Cp2);
-                f1_tmem_wait_ld();
-#pragma unroll
-                for (int q = 0; q < 16; q += 2) {
-                  const float dz0 = fmaf(x[q], sc, sh) > 0.f ? v[q] : 0.f;
-                  const float dz1 = fmaf(x[q + 1], sc, sh) > 0.f ? v[q + 1] : 0.f;
-                  db0 += dz0;
-                  db1 += dz1;
-                  dg0 = fmaf(dz0, fmaf(x[q], is, nmi), dg0);
-                  dg1 = fmaf(dz1, fmaf(x[q + 1], is, nmi), dg1);
-                  v[q] = gm * dz0;
-                  v[q + 1] = gm * dz1;
-                }
-#pragma unroll
-                for (int q = 0; q < 16; ++q)
-                  f1_sts_u16(a0 + (uint32_t)q * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(v[q])));
+                if (Cp2 == 256u) f1_ep16<256>(a0, v, thr, neg, gm, db0, db1, dx0, dx1);
+                else if (Cp2 == 64u) f1_ep16<64>(a0, v, thr, neg, gm, db0, db1, dx0, dx1);
+                else f1_ep16<128>(a0, v, thr, neg, gm, db0, db1, dx0, dx1);
               } else {
+                float x[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) x[q] = q < nvl ? f1_lds_bf16(a0 + (uint32_t)q * Cp2) : 0.f;
                 f1_tmem_wait_ld();
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                  const float dz = (q < nvl && fmaf(x[q], sc, sh) > 0.f) ? v[q] : 0.f;
+                  const float dz = (q < nvl && ((x[q] > thr) != neg)) ? v[q] : 0.f;
                   db0 += dz;
-                  dg0 = fmaf(dz, fmaf(x[q], is, nmi), dg0);
+                  dx0 = fmaf(dz, x[q], dx0);
                   if (q < nvl) f1_sts_u16(a0 + (uint32_t)q * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz)));
                 }
               }
@@ -676,15 +714,16 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const bool ok = l0 + j < nlow;
-                const float dz = (ok && fmaf(x[j], sc, sh) > 0.f) ? d4[j] : 0.f;
+                const float dz = (ok && ((x[j] > thr) != neg)) ? d4[j] : 0.f;
                 db0 += dz;
-                dg0 = fmaf(dz, fmaf(x[j], is, nmi), dg0);
+                dx0 = fmaf(dz, x[j], dx0);
                 if (ok) f1_sts_u16(a0 + (uint32_t)j * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz)));
               }
             }
           }
+          // dgamma = sum dz*xhat = istd * sum dz*x - mean*istd * sum dz
+          a_dg[c] += fmaf(e_is[c], dx0 + dx1, e_nmi[c] * (db0 + db1));
           a_db[c] += db0 + db1;
-          a_dg[c] += dg0 + dg1;
         }
         fence_proxy_async();  // G written over x -> visible to the bulk store
         tc_fence_before();
@@ -694,7 +733,10 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           mbar_arrive(&tail->g_ready[b][c]);
           mbar_arrive(&tail->d1_free[buf]);
         }
-        ++it;
+        if (++buf == d1_nbuf) {
+          buf = 0;
+          bph ^= 1u;
+        }
       }
       if (tid == 384 && i < 12) CUNET_TRACE_MARK(trace, 146 + 4 * i);
     }
@@ -713,24 +755,25 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           atomicAdd(p.gacc[ps].gstats + Cp + kl, (double)(e_gm[c] * a_dg[c]));
         }
       }
-      // ---- weight gradient: D2_c[128 k][co] -> dW[co][k] (a warp adds 32 consecutive k of one co: coalesced)
+      // ---- weight gradient: D2_c[co][k] -> dW[co][k]: lane = output channel, 32 consecutive k per thread and chunk
       mbar_wait(&tail->done, 0);
       tc_fence_after();
       if (tid == 384) CUNET_TRACE_MARK(trace, 230);
-      const int nq = L.npad >> 2;   // 16 or 32 output channels per pixel-quarter group of warps
+      const int co = k;                      // TMEM lane
       for (int c = 0; c < nchunk; ++c) {
-        const int kg = c * 128 + k;
-        const bool kok = kg < Cin && kg < L.dwc;
-        for (int j = 0; j < nq; j += 16) {
-          float v[16];
-          const int col = pq * nq + j;
-          f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)(qd * 32) << 16) + (uint32_t)col, v);
-          f1_tmem_wait_ld();
-          if (kok) {
+        const int kvalid = min(min(128, Cin - c * 128), L.dwc - c * 128);   // real input channels of this chunk
+        const int col0 = 32 * pq;
+        if (col0 >= kvalid) continue;
+        float v[32];
+        f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
+        if (col0 + 16 < kvalid)
+          f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)(qd * 32) << 16) + (uint32_t)(col0 + 16), v + 16);
+        f1_tmem_wait_ld();
+        if (co < p.Cout) {
+          float* dst = L.dw + (long)co * L.dwc + c * 128 + col0;
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (col + q < p.Cout) atomicAdd(L.dw + (long)(col + q) * L.dwc + kg, v[q]);
-          }
+          for (int q = 0; q < 32; q += 4)
+            if (col0 + q < kvalid) f1_red_add_v4(dst + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
         }
       }
       if (tid == 384) CUNET_TRACE_MARK(trace, 231);

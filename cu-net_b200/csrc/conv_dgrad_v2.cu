@@ -16,6 +16,7 @@
 #include "loaders.cuh"
 #include "host_util.h"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace cunet {
 
@@ -595,6 +596,14 @@ int cunet_conv_dgrad_v2_try(const cunet_conv_dgrad_params* p, cudaStream_t st) {
   }
   const int nchunk = (cin + 127) / 128;
   const int split = (ntiles * nchunk <= sms) ? 1 : 0;   // small problem: one CTA per (tile, chunk)
+  // The multi-tile loop of this kernel (ntiles > number of SMs: landing-ring wrap across tiles) is retired: it passes
+  // its parity cases when it runs alone, but in round 2's whole-step A/B runs it trapped (a barrier wait that never
+  // completes) within ~50 training steps whenever another kernel ran concurrently on the side stream, while the
+  // round-1 generic kernel in its place never did.  Large 1x1 ops run their backward in the fused conv_bwd1x1 kernel
+  // instead; anything else of that size takes the generic kernel (CUNET_DGRAD_V2_MULTITILE=1 re-enables this path
+  // for debugging).
+  static const bool multitile_ok = getenv("CUNET_DGRAD_V2_MULTITILE") != nullptr;
+  if (!split && ntiles > sms && !multitile_ok) return 0;
   const int grid = split ? ntiles * nchunk : (ntiles < sms ? ntiles : sms);
   const size_t smem = D2_TAIL_OFF + sizeof(D2Tail) + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_dgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
