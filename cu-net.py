@@ -164,8 +164,11 @@ def run(opt, loader=None, val_loader=None):
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     torch.manual_seed(0)
+    # --quant quan = cu-net-prev-version-wig.py: QuanOp on the weights / gradients AND the activation-quantized model
+    # (QuanInput2d with --bits_i bits in front of the 3x3 and head convs, models/cu_net_prev_version_wig.py:96-98,277-279)
+    bits_i = opt.bits_i if (opt.quant == "quan" and opt.bits_i <= 8) else 0
     net = create_cu_net(neck_size=4, growth_rate=32, init_chan_num=128, class_num=opt.class_num,
-                        layer_num=opt.layer_num, order=opt.order, loss_num=opt.loss_num, dtype=opt.dtype)
+                        layer_num=opt.layer_num, order=opt.order, loss_num=opt.loss_num, dtype=opt.dtype, bits_i=bits_i)
     history = TrainHistory()
     opt_state = resume(net, opt, history) if opt.resume_prefix else None     # host-side, before the weights move to HBM
     from cunet_b200.parallel import shard_batch

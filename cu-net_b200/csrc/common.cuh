@@ -194,6 +194,15 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Advance a shared-memory descriptor by a byte offset (a multiple of 16 that keeps the start address inside the
+// 256 KB window, so only the 14-bit start-address field changes): the MMA issuer is ONE thread, and rebuilding a
+// descriptor from scratch for every tcgen05.mma (~10 dependent integer instructions, twice per MMA) made that thread
+// the long pole of the 64-pixel-stage kernels -- 2 us to issue the 20 MMAs of a stage (in-kernel timeline of
+// conv_fwd_v3, round 2).  With this the per-MMA cost is two adds.
+__device__ __forceinline__ uint64_t sdesc_advance(uint64_t desc, uint32_t byte_off) {
+  return desc + (uint64_t)(byte_off >> 4);
+}
+
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a row tile (tile base 1024-aligned)
 __device__ __forceinline__ uint32_t tile_off(int r, int c) {
   return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));

@@ -46,6 +46,8 @@ struct F1Layout {
   int w_off, dt_off, a_off, gt_off, x_off, tail_off;
   int x_bytes;      // one x buffer (all pieces of a stage)
   int gt_bufs;      // 1 or 2 G/T landing sets
+  int dt_bufs;      // 1 or 2 gradient-operand buffers
+  int a_slots;      // 2 or 3 activation-operand slots (ring over the (stage, chunk) items)
   int split;        // 1: stage = 2 rows x 32 columns (64-wide image with an upsampled source)
   int per;          // stages per CTA
   int npad;         // gradient operand columns (Cout rounded up to 64)
@@ -57,8 +59,14 @@ struct F1Tail {
   alignas(16) uint32_t sc2[MAX_CIN / 2];   // bf16x2 BatchNorm scale / shift of the concat (transformers)
   alignas(16) uint32_t sh2[MAX_CIN / 2];
   alignas(16) uint32_t ga2[64], gb2[64], gmu2[64], gd2[64];   // bf16x2 gradient-form coefficients (GradSmem packed)
-  uint64_t w_full, dt_ready, dt_free, done;
-  uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[4], d1_free[4], a_full[2], a_free[2];
+  // per concat channel, for the epilogue thread that owns it (kept here instead of in registers: with 896 threads the
+  // register file allows 72 per thread, and 3 chunks x 7 constants spilled inside the per-pixel loop):
+  //   x: thr, y: thr1 -- ReLU / QuanInput mask  (x > thr) != neg  [&& (x < thr1) != neg]
+  //   z: gamma,  w: bit 31 neg | bit 30 up | bit 29 valid | bits 16..17 log2(C/32) | bits 0..15 byte offset of the
+  //   channel inside an x buffer
+  alignas(16) float4 ech[MAX_CIN];
+  uint64_t w_full, done, dt_ready[2], dt_free[2];
+  uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[4], d1_free[4], a_full[3], a_free[3];
   uint64_t a_done[2][F1_MAXCH], g_ready[2][F1_MAXCH];
   uint32_t tmem_base;
   int seg_start[CUNET_MAX_SEG + 1];
@@ -67,6 +75,10 @@ struct F1Tail {
   int lowmap[F1_R];            // stage row -> row of the half-resolution run
   int rowpos[F1_R];            // stage row -> position inside its 2x2 window ((h & 1) * 2 + (w & 1))
 };
+
+// the largest op of an order-1 network (320-channel up-block adapter: weights 80 KB + dT 16 KB + A slots 32 KB + one
+// G/T set 32 KB + two 28 KB x buffers = 221184 bytes) must still fit beside the tail
+static_assert(232448 - 1024 - (int)sizeof(F1Tail) >= 221184, "conv_bwd1x1: tail too large for the 320-channel op");
 
 __device__ __forceinline__ void f1_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
@@ -103,9 +115,9 @@ __device__ __forceinline__ void f1_red_add_v4(float* dst, float a, float b, floa
 }
 // 16 pixels of one channel (the thread's TMEM lane): dz = dA * [x on the active side of the ReLU threshold],
 // accumulates sum dz and sum dz*x, overwrites x in place with gamma*dz.  CP2 = bytes between consecutive pixels.
-template <int CP2>
-__device__ __forceinline__ void f1_ep16(uint32_t a0, float* v, float thr, bool neg, float gm, float& db0, float& db1,
-                                        float& dx0, float& dx1) {
+template <int CP2, bool QUANT>
+__device__ __forceinline__ void f1_ep16(uint32_t a0, float* v, float thr, float thr1, bool neg, float gm, float& db0,
+                                        float& db1, float& dx0, float& dx1) {
   float x[16];
 #define F1_LD(q) x[q] = f1_lds_bf16_o<(q) * CP2>(a0);
   F1_LD(0) F1_LD(1) F1_LD(2) F1_LD(3) F1_LD(4) F1_LD(5) F1_LD(6) F1_LD(7)
@@ -114,8 +126,8 @@ __device__ __forceinline__ void f1_ep16(uint32_t a0, float* v, float thr, bool n
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int q = 0; q < 16; q += 2) {
-    const float dz0 = ((x[q] > thr) != neg) ? v[q] : 0.f;
-    const float dz1 = ((x[q + 1] > thr) != neg) ? v[q + 1] : 0.f;
+    const float dz0 = (((x[q] > thr) != neg) && (!QUANT || ((x[q] < thr1) != neg))) ? v[q] : 0.f;
+    const float dz1 = (((x[q + 1] > thr) != neg) && (!QUANT || ((x[q + 1] < thr1) != neg))) ? v[q + 1] : 0.f;
     db0 += dz0;
     db1 += dz1;
     dx0 = fmaf(dz0, x[q], dx0);
@@ -222,8 +234,12 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
 
   if (tid == 0) {
     mbar_init(&tail->w_full, 1);
-    mbar_init(&tail->dt_ready, 8);
-    mbar_init(&tail->dt_free, 2);     // the dgrad and the wgrad MMA issuers both release the gradient operand
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->dt_ready[b], 8);
+      mbar_init(&tail->dt_free[b], 2);   // the dgrad and the wgrad MMA issuers both release the gradient operand
+    }
+    mbar_init(&tail->a_full[2], 8);
+    mbar_init(&tail->a_free[2], 1);
     mbar_init(&tail->done, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->gt_full[b], 1);
@@ -295,20 +311,12 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
   const int e = warp - 12;
   const int qd = warp & 3, pq = (e >> 2) & 3;  // epilogue: TMEM lane quarter (hardware: warp % 4), pixel quarter
   const int k = qd * 32 + lane;                // epilogue: channel inside the chunk
-  // transformer constants (coefficients stay in shared memory: tail->sc2 / sh2 / ga2 ...)
-  int cs_s[F1_MAXCH], cs_cl2[F1_MAXCH], cs_ldx[F1_MAXCH], cs_up[F1_MAXCH];
-  // epilogue constants
-  // ReLU mask of channel k: bn(x) = sc*x + sh > 0  <=>  (x > thr) != neg  with thr = -sh/sc, neg = sc < 0
-  float e_thr[F1_MAXCH], e_is[F1_MAXCH], e_nmi[F1_MAXCH], e_gm[F1_MAXCH];
-  bool e_neg[F1_MAXCH];
-  int e_ps[F1_MAXCH];
+  // transformer constants, one packed word per chunk (coefficients stay in shared memory: tail->sc2 / sh2 / ga2 ...):
+  // bit 31 valid | bit 30 upsampled source | bits 16..17 log2(C/32) | bits 0..15 byte offset of this thread's 16-byte
+  // column inside an x buffer.  (Four separate ints per chunk were spilled to local memory and reloaded in the hot loop.)
+  uint32_t cs_pk[F1_MAXCH];
 #pragma unroll
-  for (int c = 0; c < F1_MAXCH; ++c) {
-    cs_s[c] = -1; cs_cl2[c] = 0; cs_ldx[c] = 0; cs_up[c] = 0;
-    e_thr[c] = e_is[c] = e_nmi[c] = e_gm[c] = 0.f;
-    e_neg[c] = false;
-    e_ps[c] = -1;
-  }
+  for (int c = 0; c < F1_MAXCH; ++c) cs_pk[c] = 0u;
   // packed coefficient tables -> tail (they outlive the prologue area)
   for (int i = tid; i < nchunk * 64; i += F1_THREADS) {
     tail->sc2[i] = bn->sc2[i];
@@ -327,30 +335,36 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       if (c < nchunk && ch < Cin) {
         int s = 0;
         while (ch >= tail->seg_start[s + 1]) ++s;
-        cs_s[c] = s;
-        cs_cl2[c] = (ch - tail->seg_start[s]) * 2;
-        cs_ldx[c] = p.in.seg[s].C * 2;
-        cs_up[c] = p.in.seg[s].up;
+        const int C = p.in.seg[s].C;
+        cs_pk[c] = 0x80000000u | (p.in.seg[s].up ? 0x40000000u : 0u) |
+                   ((uint32_t)(C == 128 ? 2 : (C == 64 ? 1 : 0)) << 16) |
+                   (uint32_t)(tail->xoff[s] + (ch - tail->seg_start[s]) * 2);
       }
     }
   }
-  if (is_ep) {
-#pragma unroll
-    for (int c = 0; c < F1_MAXCH; ++c) {
-      const int kg = c * 128 + k;
-      if (c < nchunk && kg < Cin) {
-        int s = 0;
-        while (kg >= tail->seg_start[s + 1]) ++s;
-        e_ps[c] = s;
-        const float sc = bn->scale[kg], sh = bn->shift[kg];
-        const float inf = __int_as_float(0x7f800000);
-        e_neg[c] = sc < 0.f;
-        e_thr[c] = sc != 0.f ? -sh / sc : (sh > 0.f ? -inf : inf);   // sc == 0: the mask is the sign of the shift
-        e_is[c] = bn->istd[kg];
-        e_nmi[c] = -bn->mean[kg] * bn->istd[kg];  // xhat = x * istd - mean * istd
-        e_gm[c] = p.in.gamma[kg];
-      }
+  // epilogue table.  ReLU mask of a channel: bn(x) = sc*x + sh > 0  <=>  (x > thr) != neg  with thr = -sh/sc, neg = sc < 0;
+  // with QuanInput between the ReLU and the conv (act_bits != 0) the straight-through gradient is also zero where
+  // bn(x) >= 1:  (x < thr1) != neg  with thr1 = (1 - sh)/sc  (thr1 = -+inf otherwise, so that test is always true)
+  for (int kg = tid; kg < nchunk * 128; kg += F1_THREADS) {
+    float4 ec = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kg < Cin) {
+      int sgi = 0;
+      while (kg >= tail->seg_start[sgi + 1]) ++sgi;
+      const float sc = bn->scale[kg], sh = bn->shift[kg];
+      const float inf = __int_as_float(0x7f800000);
+      const bool neg = sc < 0.f;
+      ec.x = sc != 0.f ? -sh / sc : (sh > 0.f ? -inf : inf);   // sc == 0: the mask is the sign of the shift
+      if (p.in.act_bits && sc != 0.f) ec.y = (1.f - sh) / sc;
+      else if (p.in.act_bits) ec.y = sh < 1.f ? inf : -inf;
+      else ec.y = neg ? -inf : inf;
+      ec.z = p.in.gamma[kg];
+      const int C = p.in.seg[sgi].C;
+      const uint32_t w = (neg ? 0x80000000u : 0u) | (p.in.seg[sgi].up ? 0x40000000u : 0u) | 0x20000000u |
+                         ((uint32_t)(C == 128 ? 2 : (C == 64 ? 1 : 0)) << 16) |
+                         (uint32_t)(tail->xoff[sgi] + (kg - tail->seg_start[sgi]) * 2);
+      ec.w = __uint_as_float(w);
     }
+    tail->ech[kg] = ec;
   }
   __syncthreads();    // the coefficient area is the x landing area from here on
 
@@ -471,23 +485,30 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
     // ============================================================== dgrad MMA issuer: D1[(stage, chunk)] = W_c * dT^T
     if (lane == 0 && ns > 0) {
       const uint32_t idesc_d = make_idesc(Elem<bf16>::FMT, 128, 64, 0, 0);
-      const uint32_t wA = smem_u32(smem + L.w_off), dT = smem_u32(smem + L.dt_off);
+      const uint32_t wA = smem_u32(smem + L.w_off);
+      const uint64_t dtdesc00 = make_sdesc(smem_u32(smem + L.dt_off), 16, 1024);   // see sdesc_advance (common.cuh)
       mbar_wait(&tail->w_full, 0);
       uint32_t buf = 0, bph = 0;     // ring position of the next D1 accumulator and its use parity
       for (int i = 0; i < ns; ++i) {
-        mbar_wait(&tail->dt_ready, (uint32_t)i & 1u);
+        const uint32_t db = L.dt_bufs == 2 ? ((uint32_t)i & 1u) : 0u;
+        const uint32_t du = (uint32_t)(L.dt_bufs == 2 ? (i >> 1) : i);
+        const uint64_t dtdesc0 = sdesc_advance(dtdesc00, db * 2u * F1_SUB);
+        mbar_wait(&tail->dt_ready[db], du & 1u);
         if (i < 12) CUNET_TRACE_MARK(trace, 96 + 3 * i);
         for (int c = 0; c < nchunk; ++c) {
           const int rows = min(128, Cin - c * 128);
           mbar_wait(&tail->d1_free[buf], bph ^ 1u);
           tc_fence_after();
           const uint32_t d1 = tmem + d1_base + buf * 64u;
-          const uint32_t wc = wA + (uint32_t)tail->woff[c];
-          for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t wdesc0 = make_sdesc(wA + (uint32_t)tail->woff[c], 16, 1024);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            if (kb >= nkb) break;
+            const uint64_t wd = sdesc_advance(wdesc0, (uint32_t)(kb * rows * 128));
+            const uint64_t dd = sdesc_advance(dtdesc0, (uint32_t)(kb * F1_SUB));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma<bf16>(d1, make_sdesc(wc + kb * rows * 128 + kk * 32, 16, 1024),
-                         make_sdesc(dT + kb * F1_SUB + kk * 32, 16, 1024), idesc_d, (uint32_t)((kb | kk) != 0));
+              umma<bf16>(d1, sdesc_advance(wd, kk * 32), sdesc_advance(dd, kk * 32), idesc_d, (uint32_t)((kb | kk) != 0));
           }
           tc_commit(&tail->d1_full[buf]);
           if (c == 0 && i < 12) CUNET_TRACE_MARK(trace, 97 + 3 * i);
@@ -496,7 +517,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
             bph ^= 1u;
           }
         }
-        tc_commit(&tail->dt_free);
+        tc_commit(&tail->dt_free[db]);
         if (i < 12) CUNET_TRACE_MARK(trace, 98 + 3 * i);
       }
     }
@@ -505,23 +526,30 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
     // (output channel = TMEM lane, input channel = column: a thread of the final epilogue then holds consecutive k of
     //  one co, i.e. consecutive floats of dW[co][:], and adds them with 16-byte reductions)
     if (lane == 0 && ns > 0) {
-      const uint32_t dT = smem_u32(smem + L.dt_off), aA = smem_u32(smem + L.a_off);
-      uint32_t ai = 0;
+      const uint64_t dtdesc00 = make_sdesc_mn<bf16>(smem_u32(smem + L.dt_off), F1_SUB);
+      const uint64_t adesc0 = make_sdesc_mn<bf16>(smem_u32(smem + L.a_off), F1_SUB);
+      uint32_t slot = 0, sph = 0;     // ring position of the next activation-operand slot and its use parity
       for (int i = 0; i < ns; ++i) {
-        mbar_wait(&tail->dt_ready, (uint32_t)i & 1u);
-        for (int c = 0; c < nchunk; ++c, ++ai) {
-          const uint32_t slot = ai & 1u;
-          mbar_wait(&tail->a_full[slot], (ai >> 1) & 1u);
+        const uint32_t db = L.dt_bufs == 2 ? ((uint32_t)i & 1u) : 0u;
+        const uint32_t du = (uint32_t)(L.dt_bufs == 2 ? (i >> 1) : i);
+        const uint64_t dtdesc0 = sdesc_advance(dtdesc00, db * 2u * F1_SUB);
+        mbar_wait(&tail->dt_ready[db], du & 1u);
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(&tail->a_full[slot], sph);
           tc_fence_after();
-          const uint32_t a = aA + slot * 16384u;
+          const uint64_t ad = sdesc_advance(adesc0, slot * 16384u);
           const uint32_t idesc_w = make_idesc(Elem<bf16>::FMT, 128, (uint32_t)min(128, Cin - c * 128), 1, 1);  // MN-major both
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma<bf16>(tmem + (uint32_t)c * 128u, make_sdesc_mn<bf16>(dT + kk * 2048, F1_SUB),
-                       make_sdesc_mn<bf16>(a + kk * 2048, F1_SUB), idesc_w, (uint32_t)((i | kk) != 0));
+            umma<bf16>(tmem + (uint32_t)c * 128u, sdesc_advance(dtdesc0, kk * 2048), sdesc_advance(ad, kk * 2048),
+                       idesc_w, (uint32_t)((i | kk) != 0));
           tc_commit(&tail->a_free[slot]);
+          if (++slot == (uint32_t)L.a_slots) {
+            slot = 0;
+            sph ^= 1u;
+          }
         }
-        tc_commit(&tail->dt_free);
+        tc_commit(&tail->dt_free[db]);
       }
       tc_commit(&tail->done);
     }
@@ -529,7 +557,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
     // ============================================================== transformers (256 threads)
     const bool gcol_ok = cc * 8 < p.dy.C;
     const bool gcol_used = cc * 8 < L.npad;
-    const uint32_t dtb = smem_u32(smem + L.dt_off), ab = smem_u32(smem + L.a_off);
+    const uint32_t dtb0 = smem_u32(smem + L.dt_off), ab = smem_u32(smem + L.a_off);
     const int* lowmap = tail->lowmap;
     const int* rowpos = tail->rowpos;
     GradCoef<bf16> gcf;
@@ -541,9 +569,14 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       gcf.d = *reinterpret_cast<const uint4*>(&tail->gd2[co2]);
     }
     const int relu_on = p.in.bn_train == 2 ? 0 : 1;
-    uint32_t ai = 0;
+    ActCoef<bf16> acf_q;              // QuanInput constants (cunet_concat.act_bits), computed once
+    acf_q.set_quant(p.in.act_bits);
+    uint32_t slot = 0, sph = 0;       // ring position of the next activation-operand slot and its use parity
     for (int i = 0; i < ns; ++i) {
       const int st = st0 + i;
+      const uint32_t db = L.dt_bufs == 2 ? ((uint32_t)i & 1u) : 0u;
+      const uint32_t du = (uint32_t)(L.dt_bufs == 2 ? (i >> 1) : i);
+      const uint32_t dtb = dtb0 + db * 2u * F1_SUB;
       const int nv = split ? F1_R : min(F1_R, M - st * F1_R);
       const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
       const int gbuf = L.gt_bufs == 2 ? (i & 1) : 0;
@@ -551,7 +584,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       const uint32_t posadd = (!split && W == 64) ? (uint32_t)((st & 1) << 1) : 0u;   // image row parity (H even)
       if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 32 + 4 * i);
       mbar_wait(&tail->gt_full[gbuf], gu & 1u);
-      mbar_wait(&tail->dt_free, ((uint32_t)i & 1u) ^ 1u);   // MMAs of the previous stage no longer read the operand
+      mbar_wait(&tail->dt_free[db], (du & 1u) ^ 1u);   // the MMAs that read this operand buffer before have completed
       if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 33 + 4 * i);
       if (gcol_used) {
         const uint32_t rg = smem_u32(smem + L.gt_off + gbuf * F1_GT_BYTES) + (uint32_t)cc * 16u;
@@ -579,7 +612,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&tail->dt_ready);
+        mbar_arrive(&tail->dt_ready[db]);
         mbar_arrive(&tail->gt_free[gbuf]);
       }
       if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 34 + 4 * i);
@@ -589,28 +622,30 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
 #pragma unroll
       for (int c = 0; c < F1_MAXCH; ++c) {
         if (c >= nchunk) break;
-        const uint32_t slot = ai & 1u;
         ActCoef<bf16> acf;
         acf.sc = *reinterpret_cast<const uint4*>(&tail->sc2[(c * 128 + cc * 8) >> 1]);
         acf.sh = *reinterpret_cast<const uint4*>(&tail->sh2[(c * 128 + cc * 8) >> 1]);
         acf.relu = relu_on;
-        mbar_wait(&tail->a_free[slot], ((ai >> 1) & 1u) ^ 1u);
+        acf.qmax2 = acf_q.qmax2;
+        acf.magic2 = acf_q.magic2;
+        mbar_wait(&tail->a_free[slot], sph ^ 1u);
         const uint32_t abase = ab + slot * 16384u;
-        const int s = cs_s[c];
-        const uint32_t rx = xb + (uint32_t)(s < 0 ? 0 : tail->xoff[s]) + (uint32_t)cs_cl2[c];
-        const int ldx = cs_ldx[c];
+        const uint32_t pk = cs_pk[c];
+        const bool cvalid = (pk & 0x80000000u) != 0u, cup = (pk & 0x40000000u) != 0u;
+        const uint32_t rx = xb + (pk & 0xFFFFu);
+        const uint32_t lsh = 6u + ((pk >> 16) & 3u);      // log2(bytes per source row)
         uint4 raw[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = rb + 16 * q;
           raw[q] = make_uint4(0, 0, 0, 0);
-          if (s >= 0 && r < nv) raw[q] = f1_lds128(rx + (uint32_t)((cs_up[c] ? lowmap[r] : r) * ldx));
+          if (cvalid && r < nv) raw[q] = f1_lds128(rx + ((uint32_t)(cup ? lowmap[r] : r) << lsh));
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = rb + 16 * q;
           uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
-          if (s >= 0 && r < nv) o = acf.apply(raw[q], lo_unused);
+          if (cvalid && r < nv) o = acf.apply(raw[q], lo_unused);
           sts128(abase + (uint32_t)(cc >> 3) * F1_SUB + tile_off(r, cc & 7), o);
         }
         fence_proxy_async();
@@ -619,15 +654,18 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           mbar_arrive(&tail->a_full[slot]);
           mbar_arrive(&tail->a_done[b][c]);   // the epilogue may now overwrite this chunk's x with gamma*dz
         }
-        ++ai;
+        if (++slot == (uint32_t)L.a_slots) {
+          slot = 0;
+          sph ^= 1u;
+        }
       }
       if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 35 + 4 * i);
     }
   } else if (is_ep) {
     // ============================================================== epilogue (512 threads)
-    float a_db[F1_MAXCH], a_dg[F1_MAXCH];
+    float a_db[F1_MAXCH], a_dx[F1_MAXCH];   // per chunk: sum dz, sum dz*x of this thread's channel
 #pragma unroll
-    for (int c = 0; c < F1_MAXCH; ++c) a_db[c] = a_dg[c] = 0.f;
+    for (int c = 0; c < F1_MAXCH; ++c) a_db[c] = a_dx[c] = 0.f;
     // upsampled source: the two 8-column TMEM windows that hold the 16 children of this thread's 4 low pixels
     uint32_t upA = 0, upB = 0;
     if (W >= 32) {                 // split, or two whole rows of 32: rows 2j.. of both image rows
@@ -653,17 +691,17 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         mbar_wait(&tail->a_done[b][c], upar);     // the transformers have read this chunk's x
         if (tid == 384 && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 144 + 4 * i);
         tc_fence_after();
-        const int ps = e_ps[c];
-        if (ps >= 0) {
-          const cunet_seg& sg = p.in.seg[ps];
-          const uint32_t Cp2 = (uint32_t)sg.C * 2u;
-          const uint32_t xa = xb + (uint32_t)tail->xoff[ps] + (uint32_t)((c * 128 + k - tail->seg_start[ps]) * 2);
-          const float thr = e_thr[c], gm = e_gm[c];
-          const bool neg = e_neg[c];
+        const float4 ec = tail->ech[c * 128 + k];
+        const uint32_t ew = __float_as_uint(ec.w);
+        if (ew & 0x20000000u) {
+          const uint32_t Cp2 = 64u << ((ew >> 16) & 3u);
+          const uint32_t xa = xb + (ew & 0xFFFFu);
+          const float thr = ec.x, thr1 = ec.y, gm = ec.z;
+          const bool neg = (ew & 0x80000000u) != 0u, is_up = (ew & 0x40000000u) != 0u;
           const uint32_t tb = tmem + d1_base + buf * 64u + ((uint32_t)(qd * 32) << 16);
           float db0 = 0.f, db1 = 0.f, dx0 = 0.f, dx1 = 0.f;   // sum dz, sum dz*x (xhat applied once at the end)
           float v[16];
-          if (!sg.up) {
+          if (!is_up) {
             // this thread's 16 pixels: stage rows 16 pq .. 16 pq + 15
             const int r0 = 16 * pq;
             const int nvl = nv - r0;
@@ -671,9 +709,13 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
               f1_tmem_ld16_nowait(tb + (uint32_t)r0, v);
               const uint32_t a0 = xa + (uint32_t)r0 * Cp2;
               if (nvl >= 16) {
-                if (Cp2 == 256u) f1_ep16<256>(a0, v, thr, neg, gm, db0, db1, dx0, dx1);
-                else if (Cp2 == 64u) f1_ep16<64>(a0, v, thr, neg, gm, db0, db1, dx0, dx1);
-                else f1_ep16<128>(a0, v, thr, neg, gm, db0, db1, dx0, dx1);
+                if (p.in.act_bits) {   // only convs behind a QuanInput2d (heads: one 128-channel source)
+                  if (Cp2 == 256u) f1_ep16<256, true>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
+                  else if (Cp2 == 64u) f1_ep16<64, true>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
+                  else f1_ep16<128, true>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
+                } else if (Cp2 == 256u) f1_ep16<256, false>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
+                else if (Cp2 == 64u) f1_ep16<64, false>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
+                else f1_ep16<128, false>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
               } else {
                 float x[16];
 #pragma unroll
@@ -681,7 +723,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
                 f1_tmem_wait_ld();
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                  const float dz = (q < nvl && ((x[q] > thr) != neg)) ? v[q] : 0.f;
+                  const float dz = (q < nvl && ((x[q] > thr) != neg) && ((x[q] < thr1) != neg)) ? v[q] : 0.f;
                   db0 += dz;
                   dx0 = fmaf(dz, x[q], dx0);
                   if (q < nvl) f1_sts_u16(a0 + (uint32_t)q * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz)));
@@ -714,15 +756,14 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const bool ok = l0 + j < nlow;
-                const float dz = (ok && ((x[j] > thr) != neg)) ? d4[j] : 0.f;
+                const float dz = (ok && ((x[j] > thr) != neg) && ((x[j] < thr1) != neg)) ? d4[j] : 0.f;
                 db0 += dz;
                 dx0 = fmaf(dz, x[j], dx0);
                 if (ok) f1_sts_u16(a0 + (uint32_t)j * Cp2, __bfloat16_as_ushort(__float2bfloat16_rn(gm * dz)));
               }
             }
           }
-          // dgamma = sum dz*xhat = istd * sum dz*x - mean*istd * sum dz
-          a_dg[c] += fmaf(e_is[c], dx0 + dx1, e_nmi[c] * (db0 + db1));
+          a_dx[c] += dx0 + dx1;
           a_db[c] += db0 + db1;
         }
         fence_proxy_async();  // G written over x -> visible to the bulk store
@@ -743,16 +784,25 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
     if (ns > 0) {
 #pragma unroll
       for (int c = 0; c < F1_MAXCH; ++c) {
-        const int ps = e_ps[c];
-        if (c >= nchunk || ps < 0) continue;
         const int kg = c * 128 + k;
+        if (c >= nchunk || kg >= Cin) continue;
+        int ps = 0;
+        while (kg >= tail->seg_start[ps + 1]) ++ps;
+        const int kl = kg - tail->seg_start[ps], Cp = p.in.seg[ps].C;
+        // dgamma = sum dz*xhat = istd * (sum dz*x - mean * sum dz); mean / istd of the channel as compute_bn_coefs has them
+        const cunet_seg& sg = p.in.seg[ps];
+        const double mean = sg.stats[kl] * sg.inv_count;
+        double var = sg.stats[Cp + kl] * sg.inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float is = (float)(1.0 / sqrt(var + (double)p.in.eps));
+        const float dg = is * (a_dx[c] - (float)mean * a_db[c]);
+        const float gm = tail->ech[kg].z;
         atomicAdd(p.dbeta + kg, a_db[c]);
-        atomicAdd(p.dgamma + kg, a_dg[c]);
+        atomicAdd(p.dgamma + kg, dg);
         if (p.gacc[ps].gstats) {
           // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma)  (see conv_dgrad_v2.cu)
-          const int kl = kg - tail->seg_start[ps], Cp = p.in.seg[ps].C;
-          atomicAdd(p.gacc[ps].gstats + kl, (double)(e_gm[c] * a_db[c]));
-          atomicAdd(p.gacc[ps].gstats + Cp + kl, (double)(e_gm[c] * a_dg[c]));
+          atomicAdd(p.gacc[ps].gstats + kl, (double)(gm * a_db[c]));
+          atomicAdd(p.gacc[ps].gstats + Cp + kl, (double)(gm * dg));
         }
       }
       // ---- weight gradient: D2_c[co][k] -> dW[co][k]: lane = output channel, 32 consecutive k per thread and chunk
@@ -831,13 +881,30 @@ static int conv_bwd1x1_try(const cunet_conv_dgrad_params* d, const cunet_conv_wg
   L.w_off = 0;
   const int wbytes = cin * 128 * nkb;
   // the last chunk's weight rows are read as a full 128-row operand: keep 16 KB of readable slack behind them
-  L.dt_off = (wbytes + 1023) & ~1023;
-  L.a_off = L.dt_off + 2 * F1_SUB;
-  L.gt_off = L.a_off + 2 * 16384;
   L.x_bytes = (xbytes + 1023) & ~1023;
   if (L.x_bytes < 16384) L.x_bytes = 16384;   // the coefficient tables live there during the prologue
   const int limit = 232448 - 1024 - (int)sizeof(F1Tail);
-  L.gt_bufs = (L.gt_off + 2 * F1_GT_BYTES + 2 * L.x_bytes <= limit) ? 2 : 1;
+  // spare shared memory buys decoupling, in this order: an activation-operand slot per chunk (the transform of chunk c
+  // then waits for the wgrad MMAs of the PREVIOUS stage, not of two items ago), a second gradient-operand buffer (dT of
+  // stage i+1 is built while the MMAs of stage i still read theirs), a second G/T landing set
+  const int nchunk_h = (cin + 127) / 128;
+  const int base = ((wbytes + 1023) & ~1023) + 2 * L.x_bytes;
+  L.a_slots = 2;
+  L.dt_bufs = 1;
+  L.gt_bufs = 1;
+  auto need = [&]() { return base + L.dt_bufs * 2 * F1_SUB + L.a_slots * 16384 + L.gt_bufs * F1_GT_BYTES; };
+  if (need() > limit) return 0;
+  if (nchunk_h == 3) {
+    L.a_slots = 3;
+    if (need() > limit) L.a_slots = 2;
+  }
+  L.dt_bufs = 2;
+  if (need() > limit) L.dt_bufs = 1;
+  L.gt_bufs = 2;
+  if (need() > limit) L.gt_bufs = 1;
+  L.dt_off = (wbytes + 1023) & ~1023;
+  L.a_off = L.dt_off + L.dt_bufs * 2 * F1_SUB;
+  L.gt_off = L.a_off + L.a_slots * 16384;
   L.x_off = L.gt_off + L.gt_bufs * F1_GT_BYTES;
   L.tail_off = L.x_off + 2 * L.x_bytes;
   if (L.tail_off > limit) return 0;

@@ -203,6 +203,10 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
       const uint32_t idesc_w1 = make_idesc(Elem<bf16>::FMT, 128, 192, 1, 1);
       const uint32_t idesc_w2 = make_idesc(Elem<bf16>::FMT, 128, 128, 1, 1);
       const uint32_t wA = smem_u32(smem + B3_W_OFF), bB = smem_u32(smem + B3_B_OFF), aA = smem_u32(smem + B3_A_OFF);
+      // operand descriptors are advanced from these bases (sdesc_advance, common.cuh): one thread issues the 26 MMAs of a
+      // stage, and rebuilding every descriptor from scratch was a measurable part of its time
+      const uint64_t wdesc0 = make_sdesc(wA, 16, 1024), bdesc0 = make_sdesc(bB, 16, 1024);
+      const uint64_t amn0 = make_sdesc_mn<bf16>(aA, B3_SUB), bmn0 = make_sdesc_mn<bf16>(bB, B3_SUB);
       mbar_wait(&tail->w_full, 0);
       for (int i = 0; i < ns; ++i) {
         const uint32_t b = (uint32_t)i & 1u;
@@ -217,17 +221,17 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if (kb == 4 && kk >= 2) break;  // K index >= 288: padding
-            umma<bf16>(d1, make_sdesc(wA + kb * 16384 + kk * 32, 16, 1024),
-                       make_sdesc(bB + kb * B3_SUB + kk * 32, 16, 1024), idesc_d, (uint32_t)((kb | kk) != 0));
+            umma<bf16>(d1, sdesc_advance(wdesc0, kb * 16384 + kk * 32), sdesc_advance(bdesc0, kb * B3_SUB + kk * 32),
+                       idesc_d, (uint32_t)((kb | kk) != 0));
           }
         }
         tc_commit(&tail->d1_full[b]);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint32_t acc = (uint32_t)((i | kk) != 0);
-          const uint64_t ad = make_sdesc_mn<bf16>(aA + kk * 2048, B3_SUB);
-          umma<bf16>(tmem, ad, make_sdesc_mn<bf16>(bB + kk * 2048, B3_SUB), idesc_w1, acc);
-          umma<bf16>(tmem + 192, ad, make_sdesc_mn<bf16>(bB + 3 * B3_SUB + kk * 2048, B3_SUB), idesc_w2, acc);
+          const uint64_t ad = sdesc_advance(amn0, kk * 2048);
+          umma<bf16>(tmem, ad, sdesc_advance(bmn0, kk * 2048), idesc_w1, acc);
+          umma<bf16>(tmem + 192, ad, sdesc_advance(bmn0, 3 * B3_SUB + kk * 2048), idesc_w2, acc);
         }
         tc_commit(&tail->ops_free);
         if (i < 16) CUNET_TRACE_MARK(trace, 98 + 3 * i);
@@ -291,6 +295,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
   } else if (is_ep) {
     // ============================================================== epilogue (256 threads)
     const float gm = p.in.gamma[k];
+    // QuanInput between the ReLU and the conv (cunet_concat.act_bits): straight-through, zero where the activation >= 1
+    const float zmax = p.in.act_bits ? 1.f : __int_as_float(0x7f800000);
     float a_db = 0.f, a_dg = 0.f;
     for (int i = 0; i < ns; ++i) {
       const int m0 = (st0 + i) * B3_R, nv = min(B3_R, M - m0);
@@ -315,7 +321,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
         uint16_t gb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const bool on = fmaf(x[q], sc, sh) > 0.f && q < nval;
+          const float z = fmaf(x[q], sc, sh);
+          const bool on = z > 0.f && z < zmax && q < nval;
           const float dz = on ? v[q] : 0.f;
           a_db += dz;
           a_dg = fmaf(dz, fmaf(x[q], is, nmi), a_dg);

@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
       xn.load(src + row_n * sg.ld + cl);
       if (ga.accumulate) on.load(G + row_n * ga.ld + cl);
     }
+    // QuanInput between the ReLU and the conv (cunet_concat.act_bits): straight-through, zero where the activation >= 1
+    const float zmax = p.in.act_bits ? 1.f : __int_as_float(0x7f800000);
     for (int j = 0; j < nrow_it; ++j) {
       const Raw4<T> xc = xn, oc = on;
       const long row = row_n;
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float z = fmaf(xv[e], sc[e], sh[e]);
-          const float dz = z > 0.f ? av[e] : 0.f;
+          const float dz = (z > 0.f && z < zmax) ? av[e] : 0.f;
           a_db[e] += dz;
           a_dg[e] += dz * (xv[e] - mu[e]) * is[e];
           gv[e] = gm[e] * dz;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MIN_CTAS) conv_dgrad_kernel(con
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float z = fmaf(xv[e], sc[e], sh[e]);
-            const float dz = z > 0.f ? av[e] : 0.f;
+            const float dz = (z > 0.f && z < zmax) ? av[e] : 0.f;
             a_db[e] += dz;
             a_dg[e] += dz * (xv[e] - mu[e]) * is[e];
             gv[e] += gm[e] * dz;

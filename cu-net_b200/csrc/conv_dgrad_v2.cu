@@ -563,6 +563,7 @@ extern "C" int cunet_debug_dgrad_trace(void* buf) {
 // Returns 1 when the v2 kernel handled the call, 0 when the caller must use the generic kernel, <0 on error.
 int cunet_conv_dgrad_v2_try(const cunet_conv_dgrad_params* p, cudaStream_t st) {
   if (p->dtype != CUNET_BF16 || p->taps != 1) return 0;
+  if (p->in.act_bits) return 0;   // activation-quantized operand (wig heads): generic kernel / fused kernel
   if (p->dy.ld != p->dy.C || p->dy.C > 128 || (p->dy.C & 7)) return 0;
   if (p->CoutPad > 128) return 0;
   int cin = 0, up = 0, pieces_max = 0;

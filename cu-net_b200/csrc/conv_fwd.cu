@@ -268,6 +268,7 @@ using namespace cunet;
 
 int cunet_conv_fwd3x3_try(const cunet_conv_fwd_params* p, cudaStream_t st);  // conv_fwd3x3.cu
 int cunet_conv_fwd_v2_try(const cunet_conv_fwd_params* p, cudaStream_t st);   // conv_fwd_v2.cu
+int cunet_conv_fwd_v3_try(const cunet_conv_fwd_params* p, cudaStream_t st);   // conv_fwd_v3.cu
 
 extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   if (!p) return cunet_fail("conv_fwd: null params");
@@ -289,8 +290,11 @@ extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
   const long M = (long)p->N * p->H * p->W;
   if (M <= 0) return 0;
   if (p->taps == 1) {
-    // bf16 1x1 without pooling: persistent bulk-landing kernel
-    const int r = cunet_conv_fwd_v2_try(p, reinterpret_cast<cudaStream_t>(stream));
+    // bf16 1x1 on large maps: third-generation persistent kernel (resident weights, transposed GEMM, pooling fused)
+    int r = cunet_conv_fwd_v3_try(p, reinterpret_cast<cudaStream_t>(stream));
+    if (r != 0) return r < 0 ? r : 0;
+    // opt-in second-generation kernel (kept for A/B runs)
+    r = cunet_conv_fwd_v2_try(p, reinterpret_cast<cudaStream_t>(stream));
     if (r != 0) return r < 0 ? r : 0;
   }
   if (p->taps == 9) {

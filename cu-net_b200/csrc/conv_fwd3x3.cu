@@ -146,14 +146,18 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
         mbar_wait(&tail->acc_free[b], ((i >> 1) & 1u) ^ 1u);
         if (i < 16) CUNET_TRACE_MARK(trace, 64 + 2 * i);
         tc_fence_after();
+        // descriptors are advanced from two bases (sdesc_advance, common.cuh): the issuer is one thread and rebuilding
+        // 48 descriptors per tile from scratch was a measurable part of its time
+        const uint64_t adesc0 = make_sdesc(aA, 16, 1024), wdesc0 = make_sdesc(wB, 16, 1024);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
+          const uint64_t ady = sdesc_advance(adesc0, (uint32_t)(dy * W * 128));
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma<bf16>(tmem + b * 128u, make_sdesc(aA + kb * 32768 + dy * W * 128 + kk * 32, 16, 1024),
-                         make_sdesc(wB + (dy * 2 + kb) * 12288 + kk * 32, 16, 1024), idesc,
+              umma<bf16>(tmem + b * 128u, sdesc_advance(ady, kb * 32768 + kk * 32),
+                         sdesc_advance(wdesc0, (dy * 2 + kb) * 12288 + kk * 32), idesc,
                          (uint32_t)((dy | kb | kk) != 0));
           }
         }

@@ -350,6 +350,7 @@ int cunet_conv_fwd_v2_try(const cunet_conv_fwd_params* p, cudaStream_t st) {
   if (min_tiles < 0) return 0;
   if (p->dtype != CUNET_BF16 || p->taps != 1 || p->pool) return 0;
   if (p->in.bn_train == 2) return 0;  // identity (im2col) input of the stem: generic kernel
+  if (p->in.act_bits) return 0;       // activation-quantized operand: the other kernels
   if (p->CoutPad % 16 || p->CoutPad < 16 || p->CoutPad > 128) return 0;
   if (p->out_fp32) {
     if (p->out_ld % 8 || p->out_ld > p->CoutPad) return 0;

@@ -37,6 +37,30 @@ struct alignas(16) BnSmem {
   int seg_start[CUNET_MAX_SEG + 1];
   int cin;
   int relu;  // 1: ReLU;  0: identity input (bn_train == 2, the stem's im2col operand)
+  int act_bits;  // QuanInput between the ReLU and the conv (0: none), see ActQuant
+};
+
+// QuanInput (utils/quantize.py:47-63) on the activated operand a = relu(bn(x)) >= 0:
+//   a <- round_half_even(min(a, 1 - 2^-(b-1)) * 2^(b-1)) / 2^(b-1)
+// bf16: adding and subtracting 2^(8-b) rounds a bf16 in [0, 1) to that grid exactly (the sum has ulp 2^-(b-1) and the
+// hardware add rounds to nearest even); fp32: rintf.  Backward (dgrad epilogues): straight-through, zero where a >= 1.
+struct ActQuant {
+  int bits;
+  float qmax, scale, inv;   // 1 - 2^-(b-1), 2^(b-1), 2^-(b-1)
+  uint32_t qmax2, magic2;   // bf16x2
+  __device__ __forceinline__ void init(int b) {
+    bits = (b >= 2 && b <= 8) ? b : 0;
+    scale = (float)(1 << (bits > 0 ? bits - 1 : 0));
+    inv = 1.f / scale;
+    qmax = 1.f - inv;
+    const float magic = (float)(1 << (bits > 0 ? 8 - bits : 0));
+    qmax2 = pack_bf16x2_raw(qmax, qmax);
+    magic2 = pack_bf16x2_raw(magic, magic);
+  }
+  static __device__ __forceinline__ uint32_t pack_bf16x2_raw(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
 };
 
 __device__ __forceinline__ int concat_cin(const cunet_concat& in) {
@@ -62,6 +86,7 @@ __device__ __forceinline__ void compute_bn_coefs(const cunet_concat& in, BnSmem*
     for (int s = in.nseg; s <= CUNET_MAX_SEG; ++s) b->seg_start[s] = acc;
     b->cin = acc;
     b->relu = in.bn_train == 2 ? 0 : 1;
+    b->act_bits = in.act_bits;
   }
   const int Cin = concat_cin(in);
   for (int k2 = tid; k2 < kpad / 2; k2 += nthreads) {
@@ -199,10 +224,18 @@ template <typename T> struct ActCoef;
 template <> struct ActCoef<bf16> {
   uint4 sc, sh;
   int relu;
+  uint32_t qmax2 = 0, magic2 = 0;   // magic2 != 0: QuanInput on the activated operand (ActQuant)
+  __device__ __forceinline__ void set_quant(int act_bits) {
+    ActQuant q;
+    q.init(act_bits);
+    qmax2 = q.bits ? q.qmax2 : 0u;
+    magic2 = q.bits ? q.magic2 : 0u;
+  }
   __device__ __forceinline__ void load(const BnSmem* b, int ch) {
     sc = *reinterpret_cast<const uint4*>(&b->sc2[ch >> 1]);
     sh = *reinterpret_cast<const uint4*>(&b->sh2[ch >> 1]);
     relu = b->relu;
+    set_quant(b->act_bits);
   }
   __device__ __forceinline__ uint4 apply(const uint4& raw, uint4& lo) const {
     const uint32_t x[4] = {raw.x, raw.y, raw.z, raw.w};
@@ -216,6 +249,11 @@ template <> struct ActCoef<bf16> {
                                  *reinterpret_cast<const __nv_bfloat162*>(&s[i]),
                                  *reinterpret_cast<const __nv_bfloat162*>(&t[i]));
       if (relu) v = __hmax2(v, zero);
+      if (magic2) {
+        const __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(&magic2);
+        v = __hmin2(v, *reinterpret_cast<const __nv_bfloat162*>(&qmax2));
+        v = __hsub2(__hadd2(v, m), m);
+      }
       o[i] = *reinterpret_cast<uint32_t*>(&v);
     }
     (void)lo;
@@ -225,10 +263,16 @@ template <> struct ActCoef<bf16> {
 template <> struct ActCoef<float> {
   float4 sc, sh;
   float fl;
+  float qmax = 0.f, qscale = 0.f, qinv = 0.f;   // qscale != 0: QuanInput on the activated operand (ActQuant)
   __device__ __forceinline__ void load(const BnSmem* b, int ch) {
     sc = *reinterpret_cast<const float4*>(&b->scale[ch]);
     sh = *reinterpret_cast<const float4*>(&b->shift[ch]);
     fl = b->relu ? 0.f : -__int_as_float(0x7f800000);
+    ActQuant q;
+    q.init(b->act_bits);
+    qmax = q.qmax;
+    qscale = q.bits ? q.scale : 0.f;
+    qinv = q.inv;
   }
   __device__ __forceinline__ uint4 apply(const uint4& raw, uint4& lo) const {
     float f[4];
@@ -236,6 +280,10 @@ template <> struct ActCoef<float> {
     f[1] = fmaxf(fmaf(__uint_as_float(raw.y), sc.y, sh.y), fl);
     f[2] = fmaxf(fmaf(__uint_as_float(raw.z), sc.z, sh.z), fl);
     f[3] = fmaxf(fmaf(__uint_as_float(raw.w), sc.w, sh.w), fl);
+    if (qscale != 0.f) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f[e] = rintf(fminf(f[e], qmax) * qscale) * qinv;
+    }
     lo = Chunk<float>::pack_lo(f);
     return Chunk<float>::pack_mma(f);
   }

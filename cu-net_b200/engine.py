@@ -182,6 +182,7 @@ class Engine(object):
         cc.gamma, cc.beta = self._pp(op.norm + ".weight"), self._pp(op.norm + ".bias")
         cc.rmean, cc.rvar = self._bp(op.norm + ".running_mean"), self._bp(op.norm + ".running_var")
         cc.eps = BN_EPS
+        cc.act_bits = self.plan.quan_input_bits if op.quan_input else 0
 
     def _grad_src(self, gs, t, op):
         """Gradient of tensor t = output of op."""

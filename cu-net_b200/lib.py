@@ -27,7 +27,7 @@ class Seg(C.Structure):
 class Concat(C.Structure):
     _fields_ = [("seg", Seg * MAX_SEG), ("nseg", C.c_int), ("bn_train", C.c_int),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("rmean", C.c_void_p), ("rvar", C.c_void_p),
-                ("eps", C.c_float), ("reserved", C.c_int)]
+                ("eps", C.c_float), ("act_bits", C.c_int)]
 
 
 class ConvFwdParams(C.Structure):
@@ -120,7 +120,7 @@ def load():
 # every symbol include/cunet_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "cunet_last_error", "cunet_abi_version",
-    "cunet_conv_fwd", "cunet_debug_fwd_v2_min_tiles", "cunet_conv_dgrad", "cunet_debug_dgrad_trace", "cunet_conv_wgrad", "cunet_conv_bwd3x3", "cunet_conv_bwd1x1", "cunet_pack_weights", "cunet_pack_fwd_bytes",
+    "cunet_conv_fwd", "cunet_debug_fwd_v2_min_tiles", "cunet_debug_fwd_v3_min_rows", "cunet_conv_dgrad", "cunet_debug_dgrad_trace", "cunet_conv_wgrad", "cunet_conv_bwd3x3", "cunet_conv_bwd1x1", "cunet_pack_weights", "cunet_pack_fwd_bytes",
     "cunet_pack_dgrad_bytes", "cunet_stem_im2col", "cunet_stem_pool_fwd", "cunet_stem_bwd", "cunet_mse_decode",
     "cunet_decode_finalize", "cunet_bn_running_update", "cunet_rmsprop_step",
     "cunet_quant_forward", "cunet_quant_restore", "cunet_quant_grad", "cunet_quant_input_fwd",
@@ -152,6 +152,13 @@ def conv_fwd(params):
 def debug_fwd_v2_min_tiles(min_tiles):
     """Experiment switch of the 1x1 forward dispatch (see include/cunet_b200.h); returns the previous setting."""
     return int(load().cunet_debug_fwd_v2_min_tiles(C.c_int(min_tiles)))
+
+
+def debug_fwd_v3_min_rows(min_rows):
+    """Experiment switch of the third-generation 1x1 forward kernel; returns the previous setting."""
+    fn = load().cunet_debug_fwd_v3_min_rows
+    fn.restype = C.c_long
+    return int(fn(C.c_long(min_rows)))
 
 
 def conv_dgrad(params):

@@ -59,9 +59,10 @@ class _HeadsFn(torch.autograd.Function):
 
 class CUNetB200(nn.Module):
     def __init__(self, init_chan_num, neck_size, growth_rate, class_num, layer_num, order, loss_num,
-                 dtype="fp32", in_res=256):
+                 dtype="fp32", in_res=256, bits_i=0):
         super(CUNetB200, self).__init__()
-        self.plan = Plan(class_num, layer_num, order, loss_num, neck_size, growth_rate, init_chan_num, in_res)
+        self.plan = Plan(class_num, layer_num, order, loss_num, neck_size, growth_rate, init_chan_num, in_res,
+                         quan_input_bits=bits_i)
         self.loss_anchors = list(self.plan.anchors)
         self.layer_num = layer_num
         self.compute_dtype = dtype
@@ -174,8 +175,13 @@ class CUNetB200(nn.Module):
 
 
 def create_cu_net(neck_size, growth_rate, init_chan_num, class_num, layer_num, order, loss_num,
-                  dtype="fp32", in_res=256):
-    """models/cu_net.py:362-368 (extra keyword arguments select the compute dtype / input size)."""
+                  dtype="fp32", in_res=256, bits_i=0):
+    """models/cu_net.py:362-368 (extra keyword arguments select the compute dtype / input size).
+
+    bits_i > 0 builds the activation-quantized variant of models/cu_net_prev_version_wig.py: a QuanInput2d
+    (utils/quantize.py:47-73, bitsI bits) in front of every dense-layer 3x3 conv and every head conv (:96-98,277-279),
+    applied inside the fused convs' operand transform; together with QuanOp on the weights and gradients this is
+    the training step of cu-net-prev-version-wig.py."""
     return CUNetB200(init_chan_num=init_chan_num, neck_size=neck_size, growth_rate=growth_rate,
                      class_num=class_num, layer_num=layer_num, order=order, loss_num=loss_num,
-                     dtype=dtype, in_res=in_res)
+                     dtype=dtype, in_res=in_res, bits_i=bits_i)

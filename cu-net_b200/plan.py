@@ -119,10 +119,21 @@ class ConvOp(object):
     def cin(self):
         return sum(t.C for t, _ in self.srcs)
 
+    @property
+    def quan_input(self):
+        """True for the convs that sit behind a QuanInput2d in the wig model: dense-layer conv2 and the heads."""
+        return self.kind in ("3x3", "head")
+
 
 class Plan(object):
     def __init__(self, class_num, layer_num, order, loss_num, neck_size=4, growth_rate=32, init_chan_num=128,
-                 in_res=256):
+                 in_res=256, quan_input_bits=0):
+        """quan_input_bits: 0, or the bit width of the QuanInput2d layers of the activation-quantized ("wig") model
+        variant -- between relu.2 and conv.2 of every dense layer and between relu and conv of every head
+        (models/cu_net_prev_version_wig.py:96-98, 277-279); the fused convs apply it inside their operand transform."""
+        if quan_input_bits and not (2 <= quan_input_bits <= 8):
+            raise ValueError("quan_input_bits must be 0 or in 2..8 (the bf16 operand carries 8 significant bits)")
+        self.quan_input_bits = int(quan_input_bits)
         if order >= layer_num:
             # the reference prints and calls exit() (models/cu_net.py:285-287)
             raise SystemExit("order is larger than the layer number.")

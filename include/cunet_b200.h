@@ -50,7 +50,10 @@ typedef struct {
   const float* rmean; /* [Cin] running mean  (eval mode)               */
   const float* rvar;  /* [Cin] running var   (eval mode)               */
   float eps;
-  int reserved;
+  int act_bits;       /* 0: none.  2..8: QuanInput2d between the ReLU and the conv (utils/quantize.py:47-73;
+                         models/cu_net_prev_version_wig.py:96-98,277-279): the activated operand becomes
+                         a <- round(clamp(a, +-(1 - 2^-(bits-1))) * 2^(bits-1)) / 2^(bits-1); backward straight-through,
+                         zero where |a| >= 1 */
 } cunet_concat;
 
 /* Fused  cat -> BatchNorm -> ReLU -> conv(1x1 | 3x3 pad 1)  [-> 2x2 maxpool]  forward.
@@ -147,6 +150,10 @@ int cunet_conv_wgrad(const cunet_conv_wgrad_params* p, void* stream);
  * persistent bulk-landing kernel (csrc/conv_fwd_v2.cu); < 0 (the default) keeps the round-1 kernel.  Returns the
  * previous setting.  Also settable through the environment (CUNET_FWD_V2_MIN_TILES). */
 int cunet_debug_fwd_v2_min_tiles(int min_tiles);
+/* same for the third-generation kernel (csrc/conv_fwd_v3.cu: resident weights, transposed GEMM with per-channel
+ * statistics in registers, pooling fused): bf16 1x1 forward calls with at least min_rows pixel rows use it (default
+ * 0 = every eligible call, CUNET_FWD_V3_MIN_ROWS); negative disables.  Returns the previous setting. */
+long cunet_debug_fwd_v3_min_rows(long min_rows);
 
 /* Fused backward of the dense-layer 3x3 conv (models/cu_net.py:47-48, conv2 128 -> 32): exactly
  * cunet_conv_dgrad(d) followed by cunet_conv_wgrad(w) for the SAME op (same `in`, same `dy`), in one launch.

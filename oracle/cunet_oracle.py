@@ -110,11 +110,33 @@ def init_state(class_num, layer_num, order, seed=0, **kw):
     return sd
 
 
+class _QuanInputFn(torch.autograd.Function):
+    """QuanInput of utils/quantize.py:47-63 as a modern static Function: forward Q(C(x, bitsI), bitsI) (:52-55),
+    backward the incoming gradient with the entries where x >= 1 or x <= -1 zeroed (:58-63).  The arithmetic is pinned
+    against the REAL forward / backward bodies by tests/golden/quaninput.pt (oracle/quantize_oracle.py)."""
+
+    @staticmethod
+    def forward(ctx, x, bits):
+        from . import quantize_oracle
+        ctx.save_for_backward(x)
+        return quantize_oracle.quan_input_forward(x, bits)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import quantize_oracle
+        (x,) = ctx.saved_tensors
+        return quantize_oracle.quan_input_backward(x, g), None
+
+
 class OracleCUNet(object):
-    """Functional evaluator of the reference network over a reference-named state_dict."""
+    """Functional evaluator of the reference network over a reference-named state_dict.
+
+    quan_input_bits > 0: the activation-quantized variant (models/cu_net_prev_version_wig.py: QuanInput2d between
+    relu.2 and conv.2 of every dense layer, :96-98, and between relu and conv of every head, :277-279)."""
 
     def __init__(self, state, class_num, layer_num, order, loss_num,
-                 neck_size=4, growth_rate=32, init_chan_num=128, double_bn_update=True):
+                 neck_size=4, growth_rate=32, init_chan_num=128, double_bn_update=True, quan_input_bits=0):
+        self.quan_input_bits = quan_input_bits
         if order >= layer_num:                      # models/cu_net.py:285-287 (exit())
             raise SystemExit("order is larger than the layer number.")
         self.L, self.K, self.g = layer_num, order, growth_rate
@@ -175,6 +197,8 @@ class OracleCUNet(object):
         """_DenseLayer.forward, models/cu_net.py:52-65 (drop_rate is always 0)."""
         bott = self._cat_bn_relu_conv1x1(inputs, prefix + ".norm1", prefix + ".conv1")
         y = self._bn_relu(bott, prefix + ".norm2", False)
+        if self.quan_input_bits:                       # cu_net_prev_version_wig.py:96-98
+            y = _QuanInputFn.apply(y, self.quan_input_bits)
         return F.conv2d(y, self.state[prefix + ".conv2.weight"], padding=1)
 
     def _dense_block(self, x, i, prefix, saved, requires_skip):
@@ -244,6 +268,8 @@ class OracleCUNet(object):
             x = self._hourglass(x, i, fifo)
             if (i + 1) in self.anchors:
                 y = self._bn_relu(x, "linears.%d.norm" % i, False)
+                if self.quan_input_bits:               # cu_net_prev_version_wig.py:277-279
+                    y = _QuanInputFn.apply(y, self.quan_input_bits)
                 outs.append(F.conv2d(y, s["linears.%d.conv.weight" % i]))
         assert len(outs) == len(self.anchors)
         return outs

@@ -39,7 +39,13 @@ def bn_coeffs(stats_list, counts, gamma, beta, eps=1e-5):
     return scale, shift, mean, var
 
 
-def conv_fwd_ref(srcs, ups, n, h, w, scale, shift, weight, pool=False, dtype=torch.float32):
+def quan_act(a, bits):
+    """QuanInput forward on an activated tensor (utils/quantize.py:52-55): Q(C(a, bits), bits)."""
+    s = 2.0 ** (bits - 1)
+    return torch.round(torch.clamp(a, -1 + 1 / s, 1 - 1 / s) * s) / s
+
+
+def conv_fwd_ref(srcs, ups, n, h, w, scale, shift, weight, pool=False, dtype=torch.float32, act_bits=0):
     """srcs: list of row tensors (at h,w or h/2,w/2 when up). Returns (out_rows, pool_idx or None)."""
     xs = []
     for s, up in zip(srcs, ups):
@@ -51,6 +57,8 @@ def conv_fwd_ref(srcs, ups, n, h, w, scale, shift, weight, pool=False, dtype=tor
         xs.append(x)
     x = torch.cat(xs, 1)
     a = F.relu(x * scale.to(dtype).view(1, -1, 1, 1) + shift.to(dtype).view(1, -1, 1, 1))
+    if act_bits:
+        a = quan_act(a, act_bits)
     y = F.conv2d(a, weight.to(dtype), padding=weight.shape[-1] // 2)
     idx = None
     if pool:
@@ -106,7 +114,8 @@ def grad_src_eval(g, t, coeffs, pool_idx, n, h, w):
     return nchw_to_rows(full)
 
 
-def conv_bwd_ref(srcs, ups, n, h, w, scale, shift, mean, istd, gamma, weight, dy_rows, dtype=torch.float32):
+def conv_bwd_ref(srcs, ups, n, h, w, scale, shift, mean, istd, gamma, weight, dy_rows, dtype=torch.float32,
+                 act_bits=0):
     """Reference backward of cat->BN(train, stats held fixed)->ReLU->conv for the kernels' contract.
 
     Returns (G_contrib per source [at source resolution], dgamma, dbeta, dW).  G = gamma * dz."""
@@ -119,12 +128,17 @@ def conv_bwd_ref(srcs, ups, n, h, w, scale, shift, mean, istd, gamma, weight, dy
         xs.append(x)
     x = torch.cat(xs, 1)
     z = x * scale.to(dtype).view(1, -1, 1, 1) + shift.to(dtype).view(1, -1, 1, 1)
-    a = F.relu(z).detach().requires_grad_(True)
+    a = F.relu(z)
+    if act_bits:
+        a = quan_act(a, act_bits)      # QuanInput: the conv (and its filter gradient) see the quantized activation
+    a = a.detach().requires_grad_(True)
     wt = weight.detach().clone().to(dtype).requires_grad_(True)
     y = F.conv2d(a, wt, padding=weight.shape[-1] // 2)
     dy = rows_to_nchw(dy_rows, n, h, w, dtype)[:, :weight.shape[0]]
     da, dw = torch.autograd.grad(y, [a, wt], dy)
     dz = da * (z > 0).to(dtype)
+    if act_bits:
+        dz = dz * (z < 1).to(dtype)    # straight-through, zero where the activation is >= 1 (utils/quantize.py:58-63)
     xhat = (x - mean.view(1, -1, 1, 1).to(dtype)) * istd.view(1, -1, 1, 1).to(dtype)
     dbeta = dz.sum((0, 2, 3))
     dgamma = (dz * xhat).sum((0, 2, 3))

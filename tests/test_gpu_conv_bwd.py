@@ -53,7 +53,7 @@ def fill_grad_src(gs, cs, dy_mode):
     gs.eps = 1e-5
 
 
-def reference(cs, n, h, w, ups, dy_mode):
+def reference(cs, n, h, w, ups, dy_mode, act_bits=0):
     scale, shift, mean, var = ops_ref.bn_coeffs(cs["stats"], cs["counts"], cs["gamma"], cs["beta"])
     istd = 1.0 / torch.sqrt(var + 1e-5)
     coeffs = None if dy_mode == "plain" else ops_ref.grad_coeffs(cs["tstats"], cs["gstats"], cs["rows"])
@@ -61,7 +61,7 @@ def reference(cs, n, h, w, ups, dy_mode):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     return ops_ref.conv_bwd_ref([s.float() for s in cs["srcs"]], ups, n, h, w, scale, shift, mean, istd,
-                                cs["gamma"], cs["weight"], dy)
+                                cs["gamma"], cs["weight"], dy, act_bits=act_bits)
 
 
 CASES = [
@@ -314,3 +314,61 @@ def test_conv_bwd1x1_fused(case):
     assert _relerr(dgamma, dg_ref) < tol, "dgamma %g" % _relerr(dgamma, dg_ref)
     errw = _relerr(dw.reshape(cout, cin, -1), dw_ref.reshape(cout, cin, -1))
     assert errw < 2e-2, "%s dW rel err %g" % (name, errw)
+
+
+QBWD_CASES = [
+    # name, n, h, w, cout, taps, dy_mode, cout_pad, bits
+    ("3x3_q8", 2, 16, 16, 32, 9, "bn", None, 8),
+    ("3x3_q8_b24", 24, 64, 64, 32, 9, "bn", None, 8),
+    ("head68_q8", 2, 16, 16, 68, 1, "plain", 80, 8),
+    ("head68_q8_b24", 24, 64, 64, 68, 1, "plain", 80, 8),
+    ("head16_q4_b8", 8, 64, 64, 16, 1, "plain", 16, 4),
+]
+
+
+@pytest.mark.parametrize("case", QBWD_CASES, ids=[c[0] for c in QBWD_CASES])
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_conv_bwd_quantized_activations(case, dtype_name):
+    """Backward of a conv behind a QuanInput2d (cunet_concat.act_bits): the filter gradient contracts the QUANTIZED
+    activation, the data gradient is straight-through and zero where the activation is >= 1 (utils/quantize.py:58-63);
+    through cunet_conv_bwd3x3 / cunet_conv_bwd1x1 (fused kernels in bf16, the generic pair in fp32)."""
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.F32 if dtype_name == "f32" else lib.BF16
+    name, n, h, w, cout, taps, dy_mode, cout_pad, bits = case
+    seg_c, ups = [128], [0]
+    cs = make_case(lib, dtype, n, h, w, seg_c, ups, cout, taps, dy_mode, cout_pad, seed=11)
+    dev, td = cs["dev"], cs["td"]
+    wpack = torch.empty(lib.pack_dgrad_bytes(128, taps, cs["cout_pad"], dtype), dtype=torch.uint8, device=dev)
+    desc = lib.PackDesc(cs["weight"].data_ptr(), None, wpack.data_ptr(), cout, 128, taps, cs["cout_pad"])
+    desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).to(dev)
+    lib.pack_weights(desc_dev.data_ptr(), 1, dtype)
+    dp, wp = lib.ConvDgradParams(), lib.ConvWgradParams()
+    for q in (dp, wp):
+        fill_concat(q.inp, cs["srcs"], cs["stats"], cs["counts"], ups, cs["gamma"], cs["beta"], cs["gamma"], cs["gamma"],
+                    True, bits)
+        fill_grad_src(q.dy, cs, dy_mode)
+    x = cs["srcs"][0]
+    g0 = torch.full(x.shape, float("nan"), device=dev, dtype=td)
+    gst = torch.zeros(256, dtype=torch.float64, device=dev)
+    dp.gacc[0].G, dp.gacc[0].gstats, dp.gacc[0].ld, dp.gacc[0].accumulate = g0.data_ptr(), gst.data_ptr(), 128, 0
+    dgamma, dbeta = torch.zeros(128, device=dev), torch.zeros(128, device=dev)
+    dp.N, dp.H, dp.W, dp.taps = n, h, w, taps
+    dp.wpack_dgrad, dp.Cout, dp.CoutPad = wpack.data_ptr(), cout, cs["cout_pad"]
+    dp.dgamma, dp.dbeta, dp.dtype = dgamma.data_ptr(), dbeta.data_ptr(), dtype
+    dw = torch.zeros(cout, 128, taps, device=dev)
+    wp.N, wp.H, wp.W, wp.taps, wp.Cout = n, h, w, taps, cout
+    wp.dw, wp.nsplit, wp.dtype = dw.data_ptr(), 0, dtype
+    (lib.conv_bwd3x3 if taps == 9 else lib.conv_bwd1x1)(dp, wp)
+    torch.cuda.synchronize()
+    outs, dg_ref, db_ref, dw_ref = reference(cs, n, h, w, ups, dy_mode, act_bits=bits)
+    outs0, _, _, dw0 = reference(cs, n, h, w, ups, dy_mode)
+    tol = (4e-3 if dtype == lib.F32 else 2.5e-2) * (2 if bits < 8 else 1)
+    assert torch.isfinite(g0.float()).all()
+    eg = _relerr(g0.float(), outs[0])
+    assert eg < tol, "%s %s G rel err %g" % (name, dtype_name, eg)
+    assert _relerr(dbeta, db_ref) < tol and _relerr(dgamma, dg_ref) < tol
+    ew = _relerr(dw.reshape(cout, 128, -1), dw_ref.reshape(cout, 128, -1))
+    assert ew < tol, "%s %s dW rel err %g" % (name, dtype_name, ew)
+    # and the quantizer matters: the unquantized reference is measurably different
+    assert _relerr(outs0[0], outs[0]) > 3 * eg and _relerr(dw0.reshape(cout, 128, -1), dw_ref.reshape(cout, 128, -1)) > 3 * ew

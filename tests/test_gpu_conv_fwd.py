@@ -13,7 +13,8 @@ def _mk(lib, dtype):
     return torch.bfloat16 if dtype == lib.BF16 else torch.float32
 
 
-def fill_concat(cc, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train):
+def fill_concat(cc, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train, act_bits=0):
+    cc.act_bits = act_bits
     cc.nseg = len(srcs)
     for i, (x, st, cnt, up) in enumerate(zip(srcs, stats, counts, ups)):
         cc.seg[i].ptr = x.data_ptr()
@@ -27,7 +28,7 @@ def fill_concat(cc, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train):
 
 
 def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=True, out_fp32=False,
-                 cout_pad=None, seed=0):
+                 cout_pad=None, seed=0, act_bits=0):
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(seed)
     td = _mk(lib, dtype)
@@ -61,7 +62,7 @@ def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=
     pidx = torch.zeros(rows_out, cout, dtype=torch.uint8, device=dev) if pool else None
 
     p = lib.ConvFwdParams()
-    fill_concat(p.inp, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train)
+    fill_concat(p.inp, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train, act_bits)
     p.N, p.H, p.W, p.taps = n, h, w, taps
     p.wpack, p.Cout, p.CoutPad = wpack.data_ptr(), cout, cout_pad
     p.out, p.out_ld, p.out_fp32 = out.data_ptr(), out_ld, int(out_fp32)
@@ -81,7 +82,8 @@ def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=
         shift = (beta.double() - rmean.double() * gamma.double() * istd).float()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    ref, ridx = ops_ref.conv_fwd_ref([s.float() for s in srcs], ups, n, h, w, scale, shift, weight, pool)
+    ref, ridx = ops_ref.conv_fwd_ref([s.float() for s in srcs], ups, n, h, w, scale, shift, weight, pool,
+                                     act_bits=act_bits)
     return out, ref, out_stats, pidx, ridx
 
 
@@ -116,6 +118,17 @@ CASES = [
     ("1x1_256_b24", 24, 64, 64, [128, 128], [0, 0], 128, 1, False, True, False, None),
     ("1x1_160_eval", 5, 16, 16, [128, 32], [0, 0], 128, 1, False, False, False, None),
     ("head68_b24", 24, 64, 64, [128], [0], 68, 1, False, True, True, 80),
+    # third-generation 1x1 forward (conv_fwd_v3.cu): pooled outputs incl. the split stage geometry of 64-wide images,
+    # the other bench shapes, the 3 img/GPU strong-scaling shape, a partial last stage
+    ("1x1_192_pool_b24", 24, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, True, True, False, None),
+    ("1x1_192_pool_32_b24", 24, 32, 32, [128, 32, 32], [0, 0, 0], 128, 1, True, True, False, None),
+    ("1x1_192_pool_8", 5, 8, 8, [128, 32, 32], [0, 0, 0], 128, 1, True, True, False, None),
+    ("1x1_192_b24", 24, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, False, True, False, None),
+    ("1x1_288_up_b24", 24, 64, 64, [128, 128, 32], [1, 0, 0], 128, 1, False, True, False, None),
+    ("1x1_320_up_32_b24", 24, 32, 32, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, False, True, False, None),
+    ("1x1_320_up_16_b24", 24, 16, 16, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, False, True, False, None),
+    ("1x1_320_up_b3", 3, 64, 64, [128, 128, 32, 32], [1, 0, 0, 0], 128, 1, False, True, False, None),
+    ("head16_b16", 16, 64, 64, [128], [0], 16, 1, False, True, True, 16),
 ]
 
 
@@ -168,3 +181,65 @@ def test_conv_fwd_v2(case):
         assert (out[:, cout:] == 0).all()
     if out_stats is not None:
         assert _relerr(out_stats, ops_ref.tensor_stats(got)) < 1e-4
+
+
+V3_CASES = [c for c in CASES if c[7] == 1]     # every 1x1 case (ineligible ones fall through to the other kernels)
+
+
+@pytest.mark.parametrize("case", V3_CASES, ids=[c[0] for c in V3_CASES])
+def test_conv_fwd_v3(case):
+    """The third-generation persistent 1x1 forward kernel (conv_fwd_v3.cu) forced on at every size, bf16: outputs,
+    the per-channel statistics of the stored values, pooled outputs and argmax bytes."""
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.BF16
+    name, n, h, w, seg_c, ups, cout, taps, pool, train, out_fp32, cout_pad = case
+    old = lib.debug_fwd_v3_min_rows(0)
+    try:
+        out, ref, out_stats, pidx, ridx = run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool, train,
+                                                       out_fp32, cout_pad)
+    finally:
+        lib.debug_fwd_v3_min_rows(old)
+    got = out.float()[:, :cout]
+    assert torch.isfinite(got).all(), "kernel left unwritten / non-finite outputs"
+    err = _relerr(got, ref)
+    assert err < 1.5e-2, "%s rel err %g" % (name, err)
+    if out_fp32 and cout_pad and cout_pad > cout:
+        assert (out[:, cout:] == 0).all()
+    if out_stats is not None:
+        assert _relerr(out_stats, ops_ref.tensor_stats(got)) < 1e-4
+    if pool:
+        agree = (pidx == ridx).float().mean().item()
+        assert agree > 0.97, agree
+
+
+QUANT_CASES = [
+    # the convs that sit behind a QuanInput2d in the wig model (models/cu_net_prev_version_wig.py:96-98, 277-279)
+    ("3x3_q8", 2, 16, 16, [128], [0], 32, 9, 8, False, None),
+    ("3x3_q8_b24", 24, 64, 64, [128], [0], 32, 9, 8, False, None),
+    ("3x3_q4", 3, 8, 8, [128], [0], 32, 9, 4, False, None),
+    ("head68_q8", 2, 16, 16, [128], [0], 68, 1, 8, True, 80),
+    ("head68_q8_b24", 24, 64, 64, [128], [0], 68, 1, 8, True, 80),
+    ("head16_q8_b24", 24, 64, 64, [128], [0], 16, 1, 8, True, 16),
+]
+
+
+@pytest.mark.parametrize("case", QUANT_CASES, ids=[c[0] for c in QUANT_CASES])
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_conv_fwd_quantized_activations(case, dtype_name):
+    """cunet_concat.act_bits: QuanInput2d fused into the operand transform (csrc/loaders.cuh::ActQuant) for the convs the
+    wig model quantizes (3x3 dense-layer convs, heads), against conv(Q(C(relu(bn(x)))))."""
+    from cunet_b200 import lib
+    lib.load()
+    dtype = lib.F32 if dtype_name == "f32" else lib.BF16
+    name, n, h, w, seg_c, ups, cout, taps, bits, out_fp32, cout_pad = case
+    out, ref, out_stats, _, _ = run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, False, True, out_fp32,
+                                             cout_pad, act_bits=bits)
+    plain, _, _, _, _ = run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, False, True, out_fp32, cout_pad)
+    got = out.float()[:, :cout]
+    assert torch.isfinite(got).all()
+    err = _relerr(got, ref)
+    # a value that sits on a rounding tie of the 2^-(bits-1) grid may land on the other side (bf16 / tf32 operands)
+    tol = (4e-3 if dtype == lib.F32 else 2.5e-2) * (2 if bits < 8 else 1)
+    assert err < tol, "%s %s rel err %g" % (name, dtype_name, err)
+    assert _relerr(plain.float()[:, :cout], ref) > 3 * err, "quantization had no effect?"

@@ -15,7 +15,8 @@ def _entry():
     return m
 
 
-@pytest.mark.parametrize("extra", [[], ["--quant", "bin"], ["--no-fused", "--dtype", "fp32"]], ids=["fused", "binop", "module_api"])
+@pytest.mark.parametrize("extra", [[], ["--quant", "bin"], ["--quant", "quan", "--bits_w", "8"],
+                                   ["--no-fused", "--dtype", "fp32"]], ids=["fused", "binop", "wig", "module_api"])
 def test_entry_trains(extra):
     m = _entry()
     opt = m.parse(["--layer_num", "2", "--order", "1", "--class_num", "16", "--loss_num", "2", "--bs", "2",
