@@ -32,11 +32,12 @@
 
 namespace cunet {
 
-// warp 0 landing producer | 1 store issuer | 2 dgrad MMA issuer | 3 wgrad MMA issuer | 4-11 transformers | 12-27 epilogue.
+// warp 0 landing producer | 1 store issuer | 2 dgrad MMA issuer | 3 wgrad MMA issuer | 4-15 transformers | 16-31 epilogue.
 // 16 epilogue warps (four per TMEM lane quarter, 16 pixels each): the epilogue is a chain of dependent shared-memory
 // round trips per pixel, and with only two warps per scheduler the first version of this kernel spent 1.7 us per
 // 128-channel chunk of a 64-pixel stage waiting on instruction latency (in-kernel timeline, tools/time_bwd1x1.py).
-constexpr int F1_THREADS = 896;
+constexpr int F1_THREADS = 1024;
+constexpr int F1_TRW = 12;      // transformer warps
 constexpr int F1_R = 64;         // pixels per stage
 constexpr int F1_SUB = F1_R * 128;  // one operand sub-tile: 64 rows x 128 B
 constexpr int F1_GT_BYTES = 32768;  // one G/T landing set: G at +0, T at +16384, pool argmax bytes at +24576
@@ -235,25 +236,25 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
   if (tid == 0) {
     mbar_init(&tail->w_full, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tail->dt_ready[b], 8);
+      mbar_init(&tail->dt_ready[b], F1_TRW);
       mbar_init(&tail->dt_free[b], 2);   // the dgrad and the wgrad MMA issuers both release the gradient operand
     }
-    mbar_init(&tail->a_full[2], 8);
+    mbar_init(&tail->a_full[2], F1_TRW);
     mbar_init(&tail->a_free[2], 1);
     mbar_init(&tail->done, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->gt_full[b], 1);
-      mbar_init(&tail->gt_free[b], 8);
+      mbar_init(&tail->gt_free[b], F1_TRW);
       mbar_init(&tail->x_full[b], 1);
       mbar_init(&tail->x_free[b], 1);
       mbar_init(&tail->d1_full[b], 1);
       mbar_init(&tail->d1_free[b], 16);
       mbar_init(&tail->d1_full[b + 2], 1);
       mbar_init(&tail->d1_free[b + 2], 16);
-      mbar_init(&tail->a_full[b], 8);
+      mbar_init(&tail->a_full[b], F1_TRW);
       mbar_init(&tail->a_free[b], 1);
       for (int c = 0; c < F1_MAXCH; ++c) {
-        mbar_init(&tail->a_done[b][c], 8);
+        mbar_init(&tail->a_done[b][c], F1_TRW);
         mbar_init(&tail->g_ready[b][c], 16);
       }
     }
@@ -305,10 +306,10 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
 
-  const bool is_tr = warp >= 4 && warp < 12, is_ep = warp >= 12;
-  const int t = tid - 128;                 // transformer thread index (0..255)
-  const int cc = t & 15, rb = t >> 4;      // 16-byte column x rows rb + 16q
-  const int e = warp - 12;
+  const bool is_tr = warp >= 4 && warp < 4 + F1_TRW, is_ep = warp >= 4 + F1_TRW;
+  const int t = tid - 128;                 // transformer thread index (0..383)
+  const int cc = t & 15, rb = t >> 4;      // 16-byte column x rows rb + 24q (rb < 24)
+  const int e = warp - (4 + F1_TRW);
   const int qd = warp & 3, pq = (e >> 2) & 3;  // epilogue: TMEM lane quarter (hardware: warp % 4), pixel quarter
   const int k = qd * 32 + lane;                // epilogue: channel inside the chunk
   // transformer constants, one packed word per chunk (coefficients stay in shared memory: tail->sc2 / sh2 / ga2 ...):
@@ -590,8 +591,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         const uint32_t rg = smem_u32(smem + L.gt_off + gbuf * F1_GT_BYTES) + (uint32_t)cc * 16u;
         const uint32_t ri = smem_u32(smem + L.gt_off + gbuf * F1_GT_BYTES + 24576) + (uint32_t)cc * 8u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = rb + 16 * q;
+        for (int q = 0; q < 3; ++q) {
+          const int r = rb + 24 * q;
+          if (r >= F1_R) break;
           uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
           if (gcol_ok && r < nv) {
             GradRaw<bf16> raw;
@@ -619,9 +621,11 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       // ---- activation operand per chunk -> A slots
       mbar_wait(&tail->x_full[b], upar);
       const uint32_t xb = smem_u32(smem + L.x_off + b * L.x_bytes);
-#pragma unroll
-      for (int c = 0; c < F1_MAXCH; ++c) {
-        if (c >= nchunk) break;
+      // NOT unrolled over the chunks: unrolling tripled the code of this role (and of the epilogue below); the kernel
+      // was 198 KB of SASS and its top stall reason in ncu was "no instruction" (instruction-cache misses).  The
+      // per-chunk constants rotate through three registers instead of being indexed by a compile-time chunk number.
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
         ActCoef<bf16> acf;
         acf.sc = *reinterpret_cast<const uint4*>(&tail->sc2[(c * 128 + cc * 8) >> 1]);
         acf.sh = *reinterpret_cast<const uint4*>(&tail->sh2[(c * 128 + cc * 8) >> 1]);
@@ -630,20 +634,26 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         acf.magic2 = acf_q.magic2;
         mbar_wait(&tail->a_free[slot], sph ^ 1u);
         const uint32_t abase = ab + slot * 16384u;
-        const uint32_t pk = cs_pk[c];
+        const uint32_t pk = cs_pk[0];
+        {                                     // rotate: the next chunk's word moves to the front
+          const uint32_t t0 = cs_pk[0];
+          if (nchunk == 3) { cs_pk[0] = cs_pk[1]; cs_pk[1] = cs_pk[2]; cs_pk[2] = t0; }
+          else if (nchunk == 2) { cs_pk[0] = cs_pk[1]; cs_pk[1] = t0; }
+        }
         const bool cvalid = (pk & 0x80000000u) != 0u, cup = (pk & 0x40000000u) != 0u;
         const uint32_t rx = xb + (pk & 0xFFFFu);
         const uint32_t lsh = 6u + ((pk >> 16) & 3u);      // log2(bytes per source row)
-        uint4 raw[4];
+        uint4 raw[3];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = rb + 16 * q;
+        for (int q = 0; q < 3; ++q) {
+          const int r = rb + 24 * q;
           raw[q] = make_uint4(0, 0, 0, 0);
           if (cvalid && r < nv) raw[q] = f1_lds128(rx + ((uint32_t)(cup ? lowmap[r] : r) << lsh));
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = rb + 16 * q;
+        for (int q = 0; q < 3; ++q) {
+          const int r = rb + 24 * q;
+          if (r >= F1_R) break;
           uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
           if (cvalid && r < nv) o = acf.apply(raw[q], lo_unused);
           sts128(abase + (uint32_t)(cc >> 3) * F1_SUB + tile_off(r, cc & 7), o);
@@ -683,13 +693,12 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       const int nv = split ? F1_R : min(F1_R, M - (st0 + i) * F1_R);
       const uint32_t b = (uint32_t)i & 1u, upar = ((uint32_t)i >> 1) & 1u;
       const uint32_t xb = smem_u32(smem + L.x_off + b * L.x_bytes);
-#pragma unroll
-      for (int c = 0; c < F1_MAXCH; ++c) {
-        if (c >= nchunk) break;
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {     // not unrolled, accumulators rotate (see the transformers)
         mbar_wait(&tail->d1_full[buf], bph);
         mbar_wait(&tail->x_full[b], upar);        // completed long ago: acquires the landed x for this thread
         mbar_wait(&tail->a_done[b][c], upar);     // the transformers have read this chunk's x
-        if (tid == 384 && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 144 + 4 * i);
+        if (tid == 128 + 32 * F1_TRW && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 144 + 4 * i);
         tc_fence_after();
         const float4 ec = tail->ech[c * 128 + k];
         const uint32_t ew = __float_as_uint(ec.w);
@@ -709,10 +718,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
               f1_tmem_ld16_nowait(tb + (uint32_t)r0, v);
               const uint32_t a0 = xa + (uint32_t)r0 * Cp2;
               if (nvl >= 16) {
-                if (p.in.act_bits) {   // only convs behind a QuanInput2d (heads: one 128-channel source)
-                  if (Cp2 == 256u) f1_ep16<256, true>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
-                  else if (Cp2 == 64u) f1_ep16<64, true>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
-                  else f1_ep16<128, true>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
+                if (p.in.act_bits) {   // only convs behind a QuanInput2d: heads, one 128-channel source (host checks)
+                  f1_ep16<256, true>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
                 } else if (Cp2 == 256u) f1_ep16<256, false>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
                 else if (Cp2 == 64u) f1_ep16<64, false>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
                 else f1_ep16<128, false>(a0, v, thr, thr1, neg, gm, db0, db1, dx0, dx1);
@@ -763,13 +770,23 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
               }
             }
           }
-          a_dx[c] += dx0 + dx1;
-          a_db[c] += db0 + db1;
+          a_dx[0] += dx0 + dx1;
+          a_db[0] += db0 + db1;
+        }
+        {                                     // rotate the per-chunk accumulators: the next chunk's pair moves to the front
+          const float tb0 = a_db[0], tx0 = a_dx[0];
+          if (nchunk == 3) {
+            a_db[0] = a_db[1]; a_db[1] = a_db[2]; a_db[2] = tb0;
+            a_dx[0] = a_dx[1]; a_dx[1] = a_dx[2]; a_dx[2] = tx0;
+          } else if (nchunk == 2) {
+            a_db[0] = a_db[1]; a_db[1] = tb0;
+            a_dx[0] = a_dx[1]; a_dx[1] = tx0;
+          }
         }
         fence_proxy_async();  // G written over x -> visible to the bulk store
         tc_fence_before();
         __syncwarp();
-        if (tid == 384 && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 145 + 4 * i);
+        if (tid == 128 + 32 * F1_TRW && i < 12 && c == 0) CUNET_TRACE_MARK(trace, 145 + 4 * i);
         if (lane == 0) {
           mbar_arrive(&tail->g_ready[b][c]);
           mbar_arrive(&tail->d1_free[buf]);
@@ -779,7 +796,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           bph ^= 1u;
         }
       }
-      if (tid == 384 && i < 12) CUNET_TRACE_MARK(trace, 146 + 4 * i);
+      if (tid == 128 + 32 * F1_TRW && i < 12) CUNET_TRACE_MARK(trace, 146 + 4 * i);
     }
     if (ns > 0) {
 #pragma unroll
@@ -808,7 +825,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       // ---- weight gradient: D2_c[co][k] -> dW[co][k]: lane = output channel, 32 consecutive k per thread and chunk
       mbar_wait(&tail->done, 0);
       tc_fence_after();
-      if (tid == 384) CUNET_TRACE_MARK(trace, 230);
+      if (tid == 128 + 32 * F1_TRW) CUNET_TRACE_MARK(trace, 230);
       const int co = k;                      // TMEM lane
       for (int c = 0; c < nchunk; ++c) {
         const int kvalid = min(min(128, Cin - c * 128), L.dwc - c * 128);   // real input channels of this chunk
@@ -826,7 +843,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
             if (col0 + q < kvalid) f1_red_add_v4(dst + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
         }
       }
-      if (tid == 384) CUNET_TRACE_MARK(trace, 231);
+      if (tid == 128 + 32 * F1_TRW) CUNET_TRACE_MARK(trace, 231);
     }
   }
 
@@ -867,6 +884,7 @@ static int conv_bwd1x1_try(const cunet_conv_dgrad_params* d, const cunet_conv_wg
   if (cin > MAX_CIN || cin > 128 * F1_MAXCH) return 0;
   if ((W & (W - 1)) || (H & (H - 1)) || W > 64 || W < 4 || H < 4) return 0;
   if (up && d->dy.pooled) return 0;
+  if (d->in.act_bits && (d->in.nseg != 1 || d->in.seg[0].C != 128)) return 0;   // quantized operand: heads only
   const int split = (up && split_geo) ? 1 : 0;
   const long M = (long)d->N * H * W;
   if (M <= 0) return 1;

@@ -294,9 +294,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
         mbar_wait(&tail->d_free[buf], bph ^ 1u);
         if (i < 12) CUNET_TRACE_MARK(trace, 96 + 2 * i);
         const uint32_t d = tmem + buf * 64u;
-#pragma unroll
-        for (int c = 0; c < F3_MAXCH; ++c) {
-          if (c >= nchunk) break;
+#pragma unroll 1
+        for (int c = 0; c < nchunk; ++c) {
           mbar_wait(&tail->a_full[c], (uint32_t)i & 1u);
           tc_fence_after();
 #pragma unroll
@@ -351,9 +350,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
       mbar_wait(&tail->x_full[b], ((uint32_t)i >> 1) & 1u);
       if (t == 0 && i == 4) CUNET_TRACE_MARK(trace, 299);
       const uint32_t xb = smem_u32(smem + L.x_off + b * L.x_bytes);
-#pragma unroll
-      for (int c = 0; c < F3_MAXCH; ++c) {
-        if (c >= nchunk) break;
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {       // not unrolled (code size); the per-chunk word rotates through 3 registers
         ActCoef<bf16> acf;
         acf.sc = *reinterpret_cast<const uint4*>(&tail->sc2[(c * 128 + cc * 8) >> 1]);
         acf.sh = *reinterpret_cast<const uint4*>(&tail->sh2[(c * 128 + cc * 8) >> 1]);
@@ -363,7 +361,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
         if (t == 0 && i == 4) CUNET_TRACE_MARK(trace, 300 + 4 * c);
         mbar_wait(&tail->a_free[c], ((uint32_t)i & 1u) ^ 1u);   // MMAs of the previous stage have read this chunk
         if (t == 0 && i == 4) CUNET_TRACE_MARK(trace, 301 + 4 * c);
-        const uint32_t pk = cs_pk[c];
+        const uint32_t pk = cs_pk[0];
+        {
+          const uint32_t t0 = cs_pk[0];
+          if (nchunk == 3) { cs_pk[0] = cs_pk[1]; cs_pk[1] = cs_pk[2]; cs_pk[2] = t0; }
+          else if (nchunk == 2) { cs_pk[0] = cs_pk[1]; cs_pk[1] = t0; }
+        }
         const bool cvalid = (pk & 0x80000000u) != 0u, cup = (pk & 0x40000000u) != 0u;
         const uint32_t rx = xb + (pk & 0xFFFFu);
         const uint32_t lsh = 6u + ((pk >> 16) & 3u);      // log2(bytes per source row)
