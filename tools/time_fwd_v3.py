@@ -71,7 +71,10 @@ if __name__ == "__main__":
         for c in range(3):
             print("  chunk %d %s" % (c, ["%.2f" % v for v in t[300 + 4 * c: 304 + 4 * c]]))
         sys.exit(0)
+    want = [a for a in sys.argv[1:] if a != "trace"]
     for name, n, h, w, seg_c, ups, pool in SHAPES:
+        if want and name not in want:
+            continue
         p, keep = tf.make(n, h, w, seg_c, ups, 128, 1, pool)
         cin = sum(seg_c)
         by = sum(x.numel() * 2 for x in keep[0]) + keep[7].numel() * 2
