@@ -39,13 +39,13 @@ constexpr int B3_GT_BYTES = 12544;                  // >= (64 + 2*(64 + 1)) rows
 constexpr int B3_G_OFF = B3_X_OFF + 2 * 16384;      // landed G / T with halo, double buffered: [buf][G | T]
 constexpr int B3_TAIL_OFF = B3_G_OFF + 4 * B3_GT_BYTES;
 constexpr int B3_COEF_OFF = B3_X_OFF;               // BnSmem + GradSmem live in the x buffers during the prologue only
-constexpr int B3_STG_LD = 169;                      // dW staging [128 ci][16 co][9 taps] (+9: odd stride, == 9 mod 32)
+constexpr int B3_STG_FLOATS = 32 * 128 * 9;         // dW staging in destination order [32 co][128 ci][9 taps]
 constexpr uint32_t B3_D1_COL = 320;                 // TMEM: D2 in columns [0, 320), D1 buffers at 320 and 384
 static_assert(sizeof(BnSmem) <= 8192 && sizeof(GradSmem) <= 8192, "coefficient overlay");
-static_assert(128 * B3_STG_LD * 4 <= B3_A_OFF, "dW staging must fit the (dead) weight + operand regions");
+static_assert(B3_STG_FLOATS * 4 <= B3_TAIL_OFF, "dW staging must fit the (dead) weight / operand / landing regions");
 
 struct B3Tail {
-  uint64_t w_full, ops_ready, ops_free, done;
+  uint64_t w_full, ops_ready, ops_free, done, stores_done;
   uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[2], d1_free[2], g_ready[2];
   uint32_t tmem_base;
 };
@@ -77,7 +77,7 @@ __device__ __forceinline__ uint4 b3_lds128(uint32_t saddr) {
 }
 
 // timeline slots (CUNET_TRACE builds): stage i < 16 -> producer 0+2i, transformer 32+4i, MMA 96+3i, epilogue 144+2i,
-// store issuer 176+2i; 208: dW staging starts, 209: kernel end of the epilogue warps
+// store issuer 176+2i; 208: dW staging starts, 209: staged, 210: added to the gradient
 CUNET_TRACE_DECL(g_b3_trace)
 
 __device__ __forceinline__ void b3_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
     mbar_init(&tail->ops_ready, 8);
     mbar_init(&tail->ops_free, 1);
     mbar_init(&tail->done, 1);
+    mbar_init(&tail->stores_done, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->gt_full[b], 1);
       mbar_init(&tail->gt_free[b], 8);
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
         if (i < 16) CUNET_TRACE_MARK(trace, 177 + 2 * i);
         mbar_arrive(&tail->x_free[b]);
       }
+      mbar_arrive(&tail->stores_done);   // every G store has read its staging block: the dW epilogue may reuse the area
     }
   } else if (warp == 2) {
     // ============================================================== MMA issuer
@@ -352,38 +354,56 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
     }
     // ---- weight gradient: D2[128 ci][(tap, co)] -> dW[co][ci][tap].  A thread owns one ci (TMEM lane), but the
     // reference layout has ci * 9 + tap contiguous per co: adding straight from registers put 32 different sectors
-    // under every warp-wide red (ncu: ~30 us of the kernel, even for a 6-CTA launch).  Instead the accumulator is
-    // transposed through the (now dead) weight / operand regions, 16 output channels at a time, and every warp
-    // adds 32 consecutive floats.  All CTAs run this (uniform barriers); ns == 0 CTAs do not exist (host: grid).
-    const int et = tid - 384;
+    // under every warp-wide red (ncu, round 1: ~30 us of the kernel, even for a 6-CTA launch).  The accumulator is
+    // transposed through the (now dead) weight / operand / landing regions in ONE pass over all 32 output channels
+    // (round 2: wide tcgen05.ld, 16-byte reductions, one barrier instead of four: the epilogue of a one-stage CTA took
+    // 6.8 of its ~11 us).  All CTAs run this (uniform barriers); ns == 0 CTAs do not exist (host: grid).
     float* stg = reinterpret_cast<float*>(smem);
     if (ns > 0) {
       mbar_wait(&tail->done, 0);
       tc_fence_after();
     }
+    mbar_wait(&tail->stores_done, 0);
     if (tid == 384) CUNET_TRACE_MARK(trace, 208);
-#pragma unroll 1
-    for (int hh = 0; hh < 2 && ns > 0; ++hh) {
-      for (int j = hf; j < 18; j += 2) {
-        const int tap = j >> 1, c8 = (j & 1) * 8;
-        float v[8];
-        tmem_ld8(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(tap * 32 + hh * 16 + c8), v);
+    if (ns > 0) {
+      // this thread's taps: hf == 0 -> 0..4, hf == 1 -> 5..8; per tap 32 output channels = two 16-column loads
+      const int t0 = hf ? 5 : 0, t1 = hf ? 9 : 5;
+      for (int tap = t0; tap < t1; ++tap) {
+        float v[32];
+        const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(tap * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+              "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+            : "r"(ta));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+              "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+            : "r"(ta + 16u));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int q = 0; q < 8; ++q) stg[k * B3_STG_LD + (c8 + q) * 9 + tap] = v[q];
+        for (int q = 0; q < 32; ++q) stg[q * 1152 + k * 9 + tap] = v[q];   // destination order [co][ci][tap]; lanes 9 words apart
       }
-      b3_named_bar(3, 256);
-      float* dst = dw + (long)hh * 16 * 1152;
-      for (int idx = et; idx < 16 * 1152; idx += 256) {
-        const int c16 = idx / 1152, r = idx - c16 * 1152;
-        const int ci = r / 9, tap = r - ci * 9;
-        atomicAdd(dst + idx, stg[ci * B3_STG_LD + c16 * 9 + tap]);
-      }
-      b3_named_bar(3, 256);
     }
     if (tid == 384) CUNET_TRACE_MARK(trace, 209);
   }
 
+  // every role is done and the staged dW is complete: ALL 640 threads add it to the fp32 gradient (the add loop is
+  // instruction-bound -- 36864 floats per CTA -- and ran 7 us on the 8 epilogue warps alone)
   tc_fence_before();
+  __syncthreads();
+  if (ns > 0) {
+    const float* stg = reinterpret_cast<const float*>(smem);
+    // the staged block is in destination order: 16-byte loads, 16-byte reductions (the first version of this loop rebuilt
+    // (co, ci, tap) from the index with two integer divisions per element and took 6 us per CTA)
+    for (int idx = tid * 4; idx < 32 * 1152; idx += B3_THREADS * 4) {
+      const float4 o = *reinterpret_cast<const float4*>(stg + idx);
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dw + idx), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                   : "memory");
+    }
+  }
+  if (tid == 384) CUNET_TRACE_MARK(trace, 210);
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }

@@ -55,7 +55,7 @@ def trace_bwd3x3():
     show("mma", t, "stage", 96, 3, ["operands ready", "D1 free", "issued"])
     show("epilogue", t, "stage", 144, 2, ["D1 full", "done"])
     show("store", t, "stage", 176, 2, ["G ready", "store read done"])
-    print("  dW staging starts %.1f, epilogue warps done %.1f" % (t[208], t[209]))
+    print("  dW staging starts %.1f, staged %.1f, added to the gradient %.1f" % (t[208], t[209], t[210]))
 
 
 def trace_fwd(kind):
