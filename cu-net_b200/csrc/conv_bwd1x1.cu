@@ -294,17 +294,102 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
     tail->rowpos[r] = ps;
   }
   if (warp == 2) tmem_alloc(&tail->tmem_base, 512);
+  __syncthreads();   // barrier inits and the static tables above are visible to every warp (warp 0 takes no part in the
+                     // coefficient-phase barriers below); still before griddepcontrol.wait, i.e. under the previous kernel
   griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
   griddep_launch();
-  // BatchNorm / gradient coefficients: computed in the (not yet used) x landing area, then kept in registers per role
-  BnSmem* bn = reinterpret_cast<BnSmem*>(smem + L.x_off);
-  GradSmem* gc = reinterpret_cast<GradSmem*>(smem + L.x_off + 8192);
-  compute_bn_coefs(p.in, bn, nchunk * 128, tid, F1_THREADS);
-  compute_grad_coefs(p.dy, gc, tid, F1_THREADS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tail->tmem_base;
+  // landing of one stage (thread 0 only): G / T (/ argmax) of the output, then the source pieces
+  auto land_stage = [&](int i) {
+    const char* gsrc = reinterpret_cast<const char*>(p.dy.g);
+    const char* tsrc = reinterpret_cast<const char*>(p.dy.t);
+      const F1Geo g = f1_geo(st0 + i, M, W, split, need_low);
+      // ---- G / T (/ argmax) of the output
+      const int gbuf = L.gt_bufs == 2 ? (i & 1) : 0;
+      const uint32_t gu = (uint32_t)(L.gt_bufs == 2 ? (i >> 1) : i);
+      mbar_wait(&tail->gt_free[gbuf], (gu & 1u) ^ 1u);
+      if (i < 12) CUNET_TRACE_MARK(trace, 0 + 2 * i);
+      uint8_t* gdst = smem + L.gt_off + gbuf * F1_GT_BYTES;
+      if (p.dy.pooled) {
+        const uint32_t gb = (uint32_t)(g.nlow * ldo), ib = (uint32_t)(g.nlow * p.dy.C);
+        mbar_arrive_expect_tx(&tail->gt_full[gbuf], 2u * gb + ib);
+        bulk_g2s(gdst, gsrc + (long)g.low0 * ldo, gb, &tail->gt_full[gbuf]);
+        bulk_g2s(gdst + 16384, tsrc + (long)g.low0 * ldo, gb, &tail->gt_full[gbuf]);
+        bulk_g2s(gdst + 24576, p.dy.pool_idx + (long)g.low0 * p.dy.C, ib, &tail->gt_full[gbuf]);
+      } else {
+        const uint32_t nt = p.dy.mode == 1 ? 2u : 1u;
+        if (split) {
+          const uint32_t rb32 = (uint32_t)(32 * ldo);
+          mbar_arrive_expect_tx(&tail->gt_full[gbuf], 2u * nt * rb32);
+          bulk_g2s(gdst, gsrc + (long)g.p0 * ldo, rb32, &tail->gt_full[gbuf]);
+          bulk_g2s(gdst + rb32, gsrc + (long)g.p1 * ldo, rb32, &tail->gt_full[gbuf]);
+          if (nt == 2) {
+            bulk_g2s(gdst + 16384, tsrc + (long)g.p0 * ldo, rb32, &tail->gt_full[gbuf]);
+            bulk_g2s(gdst + 16384 + rb32, tsrc + (long)g.p1 * ldo, rb32, &tail->gt_full[gbuf]);
+          }
+        } else {
+          const uint32_t gb = (uint32_t)(g.nv * ldo);
+          mbar_arrive_expect_tx(&tail->gt_full[gbuf], nt * gb);
+          bulk_g2s(gdst, gsrc + (long)g.p0 * ldo, gb, &tail->gt_full[gbuf]);
+          if (nt == 2) bulk_g2s(gdst + 16384, tsrc + (long)g.p0 * ldo, gb, &tail->gt_full[gbuf]);
+        }
+      }
+      // ---- the source pieces
+      const uint32_t b = (uint32_t)i & 1u;
+      mbar_wait(&tail->x_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+      if (i < 12) CUNET_TRACE_MARK(trace, 1 + 2 * i);
+      uint32_t xtot = 0;
+      for (int s = 0; s < p.in.nseg; ++s) {
+        const cunet_seg& sg = p.in.seg[s];
+        xtot += (uint32_t)((sg.up ? g.nlow : g.nv) * sg.C * 2);
+      }
+      mbar_arrive_expect_tx(&tail->x_full[b], xtot);
+      uint8_t* xdst = smem + L.x_off + b * L.x_bytes;
+      for (int s = 0; s < p.in.nseg; ++s) {
+        const cunet_seg& sg = p.in.seg[s];
+        const char* src = reinterpret_cast<const char*>(sg.ptr);
+        const int Cp2 = sg.C * 2;
+        if (sg.up) {
+          bulk_g2s(xdst + tail->xoff[s], src + (long)g.low0 * Cp2, (uint32_t)(g.nlow * Cp2), &tail->x_full[b]);
+        } else if (split) {
+          bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
+          bulk_g2s(xdst + tail->xoff[s] + 32 * Cp2, src + (long)g.p1 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
+        } else {
+          bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(g.nv * Cp2), &tail->x_full[b]);
+        }
+      }
+
+  };
+  // Warp 0 is the landing producer and needs no coefficient: its thread issues the weight image and then runs its whole
+  // landing loop right away; warps 1.. compute the coefficients behind NAMED barriers that do not include warp 0.
+  if (tid == 0 && ns > 0) {
+    // resident dgrad weight image: per chunk and K block only the rows that hold real input channels
+    uint32_t wtot = 0;
+    for (int c = 0; c < nchunk; ++c) wtot += (uint32_t)(min(128, Cin - c * 128) * 128 * nkb);
+    mbar_arrive_expect_tx(&tail->w_full, wtot);
+    for (int c = 0; c < nchunk; ++c) {
+      const int rows = min(128, Cin - c * 128);
+      for (int kb = 0; kb < nkb; ++kb)
+        bulk_g2s(smem + L.w_off + tail->woff[c] + kb * rows * 128,
+                 reinterpret_cast<const char*>(p.wpack_dgrad) + ((size_t)c * nkb + kb) * 16384, (uint32_t)(rows * 128),
+                 &tail->w_full);
+    }
+    for (int i = 0; i < ns; ++i) land_stage(i);
+  }
+  // BatchNorm / gradient coefficients: computed in the (not yet used) activation-operand slots, then copied into the
+  // tail tables.  NOT in the landing areas: thread 0 issues the weight image and stage 0's landings before this
+  // phase (land_stage above), so that their HBM latency overlaps it.
+  BnSmem* bn = reinterpret_cast<BnSmem*>(smem + L.a_off);
+  GradSmem* gc = reinterpret_cast<GradSmem*>(smem + L.a_off + 8192);
+  const int tq = tid - 32;                 // thread index among warps 1.. (the warps that share the coefficient phase)
+  constexpr int TQN = F1_THREADS - 32;
+  if (warp > 0) {
+    compute_bn_coefs(p.in, bn, nchunk * 128, tq, TQN);
+    compute_grad_coefs(p.dy, gc, tq, TQN);
+    tc_fence_before();
+    f1_named_bar(1, TQN);
+    tc_fence_after();
+  }
+  const uint32_t tmem = warp > 0 ? tail->tmem_base : 0u;
 
   const bool is_tr = warp >= 4 && warp < 4 + F1_TRW, is_ep = warp >= 4 + F1_TRW;
   const int t = tid - 128;                 // transformer thread index (0..383)
@@ -319,15 +404,15 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
 #pragma unroll
   for (int c = 0; c < F1_MAXCH; ++c) cs_pk[c] = 0u;
   // packed coefficient tables -> tail (they outlive the prologue area)
-  for (int i = tid; i < nchunk * 64; i += F1_THREADS) {
+  for (int i = tq; warp > 0 && i < nchunk * 64; i += TQN) {
     tail->sc2[i] = bn->sc2[i];
     tail->sh2[i] = bn->sh2[i];
   }
-  if (tid < 64) {
-    tail->ga2[tid] = gc->a2[tid];
-    tail->gb2[tid] = gc->b2[tid];
-    tail->gmu2[tid] = gc->mu2[tid];
-    tail->gd2[tid] = gc->d2[tid];
+  if (warp > 0 && tq < 64) {
+    tail->ga2[tq] = gc->a2[tq];
+    tail->gb2[tq] = gc->b2[tq];
+    tail->gmu2[tq] = gc->mu2[tq];
+    tail->gd2[tq] = gc->d2[tq];
   }
   if (is_tr) {
 #pragma unroll
@@ -346,7 +431,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
   // epilogue table.  ReLU mask of a channel: bn(x) = sc*x + sh > 0  <=>  (x > thr) != neg  with thr = -sh/sc, neg = sc < 0;
   // with QuanInput between the ReLU and the conv (act_bits != 0) the straight-through gradient is also zero where
   // bn(x) >= 1:  (x < thr1) != neg  with thr1 = (1 - sh)/sc  (thr1 = -+inf otherwise, so that test is always true)
-  for (int kg = tid; kg < nchunk * 128; kg += F1_THREADS) {
+  for (int kg = tq; warp > 0 && kg < nchunk * 128; kg += TQN) {
     float4 ec = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kg < Cin) {
       int sgi = 0;
@@ -367,82 +452,10 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
     }
     tail->ech[kg] = ec;
   }
-  __syncthreads();    // the coefficient area is the x landing area from here on
+  if (warp > 0) f1_named_bar(1, TQN);    // tables complete; the operand slots (coefficient scratch) may be overwritten
 
   if (warp == 0) {
-    // ============================================================== landing producer
-    if (lane == 0 && ns > 0) {
-      // resident dgrad weight image: per chunk and K block only the rows that hold real input channels
-      uint32_t wtot = 0;
-      for (int c = 0; c < nchunk; ++c) wtot += (uint32_t)(min(128, Cin - c * 128) * 128 * nkb);
-      mbar_arrive_expect_tx(&tail->w_full, wtot);
-      for (int c = 0; c < nchunk; ++c) {
-        const int rows = min(128, Cin - c * 128);
-        for (int kb = 0; kb < nkb; ++kb)
-          bulk_g2s(smem + L.w_off + tail->woff[c] + kb * rows * 128,
-                   reinterpret_cast<const char*>(p.wpack_dgrad) + ((size_t)c * nkb + kb) * 16384, (uint32_t)(rows * 128),
-                   &tail->w_full);
-      }
-      const char* gsrc = reinterpret_cast<const char*>(p.dy.g);
-      const char* tsrc = reinterpret_cast<const char*>(p.dy.t);
-      for (int i = 0; i < ns; ++i) {
-        const F1Geo g = f1_geo(st0 + i, M, W, split, need_low);
-        // ---- G / T (/ argmax) of the output
-        const int gbuf = L.gt_bufs == 2 ? (i & 1) : 0;
-        const uint32_t gu = (uint32_t)(L.gt_bufs == 2 ? (i >> 1) : i);
-        mbar_wait(&tail->gt_free[gbuf], (gu & 1u) ^ 1u);
-        if (i < 12) CUNET_TRACE_MARK(trace, 0 + 2 * i);
-        uint8_t* gdst = smem + L.gt_off + gbuf * F1_GT_BYTES;
-        if (p.dy.pooled) {
-          const uint32_t gb = (uint32_t)(g.nlow * ldo), ib = (uint32_t)(g.nlow * p.dy.C);
-          mbar_arrive_expect_tx(&tail->gt_full[gbuf], 2u * gb + ib);
-          bulk_g2s(gdst, gsrc + (long)g.low0 * ldo, gb, &tail->gt_full[gbuf]);
-          bulk_g2s(gdst + 16384, tsrc + (long)g.low0 * ldo, gb, &tail->gt_full[gbuf]);
-          bulk_g2s(gdst + 24576, p.dy.pool_idx + (long)g.low0 * p.dy.C, ib, &tail->gt_full[gbuf]);
-        } else {
-          const uint32_t nt = p.dy.mode == 1 ? 2u : 1u;
-          if (split) {
-            const uint32_t rb32 = (uint32_t)(32 * ldo);
-            mbar_arrive_expect_tx(&tail->gt_full[gbuf], 2u * nt * rb32);
-            bulk_g2s(gdst, gsrc + (long)g.p0 * ldo, rb32, &tail->gt_full[gbuf]);
-            bulk_g2s(gdst + rb32, gsrc + (long)g.p1 * ldo, rb32, &tail->gt_full[gbuf]);
-            if (nt == 2) {
-              bulk_g2s(gdst + 16384, tsrc + (long)g.p0 * ldo, rb32, &tail->gt_full[gbuf]);
-              bulk_g2s(gdst + 16384 + rb32, tsrc + (long)g.p1 * ldo, rb32, &tail->gt_full[gbuf]);
-            }
-          } else {
-            const uint32_t gb = (uint32_t)(g.nv * ldo);
-            mbar_arrive_expect_tx(&tail->gt_full[gbuf], nt * gb);
-            bulk_g2s(gdst, gsrc + (long)g.p0 * ldo, gb, &tail->gt_full[gbuf]);
-            if (nt == 2) bulk_g2s(gdst + 16384, tsrc + (long)g.p0 * ldo, gb, &tail->gt_full[gbuf]);
-          }
-        }
-        // ---- the source pieces
-        const uint32_t b = (uint32_t)i & 1u;
-        mbar_wait(&tail->x_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
-        if (i < 12) CUNET_TRACE_MARK(trace, 1 + 2 * i);
-        uint32_t xtot = 0;
-        for (int s = 0; s < p.in.nseg; ++s) {
-          const cunet_seg& sg = p.in.seg[s];
-          xtot += (uint32_t)((sg.up ? g.nlow : g.nv) * sg.C * 2);
-        }
-        mbar_arrive_expect_tx(&tail->x_full[b], xtot);
-        uint8_t* xdst = smem + L.x_off + b * L.x_bytes;
-        for (int s = 0; s < p.in.nseg; ++s) {
-          const cunet_seg& sg = p.in.seg[s];
-          const char* src = reinterpret_cast<const char*>(sg.ptr);
-          const int Cp2 = sg.C * 2;
-          if (sg.up) {
-            bulk_g2s(xdst + tail->xoff[s], src + (long)g.low0 * Cp2, (uint32_t)(g.nlow * Cp2), &tail->x_full[b]);
-          } else if (split) {
-            bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
-            bulk_g2s(xdst + tail->xoff[s] + 32 * Cp2, src + (long)g.p1 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
-          } else {
-            bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(g.nv * Cp2), &tail->x_full[b]);
-          }
-        }
-      }
-    }
+    // landing producer: done above
   } else if (warp == 1) {
     // ============================================================== G store issuer
     if (lane == 0) {
@@ -811,7 +824,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         const double mean = sg.stats[kl] * sg.inv_count;
         double var = sg.stats[Cp + kl] * sg.inv_count - mean * mean;
         if (var < 0.0) var = 0.0;
-        const float is = (float)(1.0 / sqrt(var + (double)p.in.eps));
+        const float is = (float)inv_sqrt_f64(var + (double)p.in.eps);
         const float dg = is * (a_dx[c] - (float)mean * a_db[c]);
         const float gm = tail->ech[kg].z;
         atomicAdd(p.dbeta + kg, a_db[c]);

@@ -86,6 +86,7 @@ __device__ __forceinline__ void f3_tmem_ld8_nowait(uint32_t taddr, float* v) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void f3_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void f3_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct F3Geo {
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
   for (int s = 0; s < p.in.nseg; ++s) any_up |= p.in.seg[s].up;
   const int need_low = any_up | p.pool;
   CUNET_TRACE_LOAD(trace, g_f3_trace)
+  if (tid == 0) CUNET_TRACE_MARK(trace, 296);
 
   if (tid == 0) {
     mbar_init(&tail->w_full, 1);
@@ -200,20 +202,65 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
     tail->lowmap[r] = lm;
   }
   if (warp == 2) tmem_alloc(&tail->tmem_base, 256);
+  __syncthreads();   // barrier inits and the static tables above are visible to every warp (warp 0 takes no part in the
+                     // coefficient-phase barriers below); still before griddepcontrol.wait, i.e. under the previous kernel
   griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
   griddep_launch();
-  BnSmem* bn = reinterpret_cast<BnSmem*>(smem + L.x_off);   // the x landing area is not in use yet
-  compute_bn_coefs(p.in, bn, nchunk * 128, tid, F3_THREADS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tail->tmem_base;
-  for (int i = tid; i < nchunk * 64; i += F3_THREADS) {
-    tail->sc2[i] = bn->sc2[i];
-    tail->sh2[i] = bn->sh2[i];
+  if (tid == 0) CUNET_TRACE_MARK(trace, 297);
+  // landing of one stage's source pieces (thread 0 only)
+  auto land_stage = [&](int i) {
+    const F3Geo g = f3_geo(st0 + i, M, W, split, need_low);
+    const uint32_t b = (uint32_t)i & 1u;
+    mbar_wait(&tail->x_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+    if (i < 12) CUNET_TRACE_MARK(trace, 0 + i);
+    uint32_t xtot = 0;
+    for (int s = 0; s < p.in.nseg; ++s) {
+      const cunet_seg& sg = p.in.seg[s];
+      xtot += (uint32_t)((sg.up ? g.nlow : g.nv) * sg.C * 2);
+    }
+    mbar_arrive_expect_tx(&tail->x_full[b], xtot);
+    uint8_t* xdst = smem + L.x_off + b * L.x_bytes;
+    for (int s = 0; s < p.in.nseg; ++s) {
+      const cunet_seg& sg = p.in.seg[s];
+      const char* src = reinterpret_cast<const char*>(sg.ptr);
+      const int Cp2 = sg.C * 2;
+      if (sg.up) {
+        bulk_g2s(xdst + tail->xoff[s], src + (long)g.low0 * Cp2, (uint32_t)(g.nlow * Cp2), &tail->x_full[b]);
+      } else if (split) {
+        bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
+        bulk_g2s(xdst + tail->xoff[s] + 32 * Cp2, src + (long)g.p1 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
+      } else {
+        bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(g.nv * Cp2), &tail->x_full[b]);
+      }
+    }
+  };
+  // Warp 0 is the landing producer and needs no BatchNorm coefficient: its thread starts issuing the weight image
+  // and the source pieces right away, while warps 1.. compute the coefficients behind a NAMED barrier that does not
+  // include warp 0 (with a CTA-wide barrier here everybody waited ~2 us for thread 0's serial issue work; the
+  // coefficient scratch lives in the operand area, not in the x landing area, for the same reason).
+  uint32_t tmem = 0;
+  int relu_on = 1;
+  if (warp == 0) {
+    if (lane == 0 && ns > 0) {
+      mbar_arrive_expect_tx(&tail->w_full, (uint32_t)nkb * wblk);
+      bulk_g2s(smem + L.w_off, p.wpack, (uint32_t)nkb * wblk, &tail->w_full);
+      for (int i = 0; i < ns; ++i) land_stage(i);
+    }
+  } else {
+    BnSmem* bn = reinterpret_cast<BnSmem*>(smem + L.a_off);   // the operand area is not in use yet
+    compute_bn_coefs(p.in, bn, nchunk * 128, tid - 32, F3_THREADS - 32);
+    tc_fence_before();
+    f3_named_bar(1, F3_THREADS - 32);
+    tc_fence_after();
+    if (tid == 32) CUNET_TRACE_MARK(trace, 298);
+    tmem = tail->tmem_base;
+    for (int i = tid - 32; i < nchunk * 64; i += F3_THREADS - 32) {
+      tail->sc2[i] = bn->sc2[i];
+      tail->sh2[i] = bn->sh2[i];
+    }
+    relu_on = bn->relu;
+    f3_named_bar(1, F3_THREADS - 32);
   }
-  const int relu_on = bn->relu;
-  __syncthreads();
 
   const bool is_tr = warp >= 4 && warp < 20, is_ep = warp >= 20;
   const int t = tid - 128;                     // transformer thread index (0..511)
@@ -223,37 +270,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
   const int co = qd * 32 + lane;               // epilogue: output channel = TMEM lane
 
   if (warp == 0) {
-    // ============================================================== landing producer
-    if (lane == 0 && ns > 0) {
-      mbar_arrive_expect_tx(&tail->w_full, (uint32_t)nkb * wblk);
-      bulk_g2s(smem + L.w_off, p.wpack, (uint32_t)nkb * wblk, &tail->w_full);
-      for (int i = 0; i < ns; ++i) {
-        const F3Geo g = f3_geo(st0 + i, M, W, split, need_low);
-        const uint32_t b = (uint32_t)i & 1u;
-        mbar_wait(&tail->x_free[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
-        if (i < 12) CUNET_TRACE_MARK(trace, 0 + i);
-        uint32_t xtot = 0;
-        for (int s = 0; s < p.in.nseg; ++s) {
-          const cunet_seg& sg = p.in.seg[s];
-          xtot += (uint32_t)((sg.up ? g.nlow : g.nv) * sg.C * 2);
-        }
-        mbar_arrive_expect_tx(&tail->x_full[b], xtot);
-        uint8_t* xdst = smem + L.x_off + b * L.x_bytes;
-        for (int s = 0; s < p.in.nseg; ++s) {
-          const cunet_seg& sg = p.in.seg[s];
-          const char* src = reinterpret_cast<const char*>(sg.ptr);
-          const int Cp2 = sg.C * 2;
-          if (sg.up) {
-            bulk_g2s(xdst + tail->xoff[s], src + (long)g.low0 * Cp2, (uint32_t)(g.nlow * Cp2), &tail->x_full[b]);
-          } else if (split) {
-            bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
-            bulk_g2s(xdst + tail->xoff[s] + 32 * Cp2, src + (long)g.p1 * Cp2, (uint32_t)(32 * Cp2), &tail->x_full[b]);
-          } else {
-            bulk_g2s(xdst + tail->xoff[s], src + (long)g.p0 * Cp2, (uint32_t)(g.nv * Cp2), &tail->x_full[b]);
-          }
-        }
-      }
-    }
+    // landing producer: done above
   } else if (warp == 1) {
     // ============================================================== output store issuer
     if (lane == 0) {

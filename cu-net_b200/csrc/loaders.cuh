@@ -63,6 +63,17 @@ struct ActQuant {
   }
 };
 
+// 1 / sqrt(v) in double: fp32 rsqrt as the seed, two Newton steps in fp64 (relative error < 1e-15).  The straight
+// `1.0 / sqrt(v)` is a double-precision square root plus a double-precision division -- two long software sequences on
+// a GPU whose fp64 rate is a small fraction of fp32 -- and EVERY conv launch computes it per input channel in its
+// prologue, after griddepcontrol.wait, i.e. on the critical path of the ~630-launch chain of a step.
+__device__ __forceinline__ double inv_sqrt_f64(double v) {
+  double y = (double)rsqrtf((float)v);
+  y = y * (1.5 - 0.5 * v * y * y);
+  y = y * (1.5 - 0.5 * v * y * y);
+  return y;
+}
+
 __device__ __forceinline__ int concat_cin(const cunet_concat& in) {
   int c = 0;
   for (int s = 0; s < in.nseg; ++s) c += in.seg[s].C;
@@ -115,7 +126,7 @@ __device__ __forceinline__ void compute_bn_coefs(const cunet_concat& in, BnSmem*
           mean = in.rmean[k];
           var = in.rvar[k];
         }
-        const double istd = 1.0 / sqrt(var + (double)in.eps);
+        const double istd = inv_sqrt_f64(var + (double)in.eps);
         const double g = in.gamma[k];
         sc = (float)(g * istd);
         sh = (float)((double)in.beta[k] - mean * g * istd);
@@ -314,7 +325,7 @@ __device__ __forceinline__ void compute_grad_coefs(const cunet_grad_src& gs, Gra
         const double mean = gs.stats[c] * n_inv;
         double var = gs.stats[gs.C + c] * n_inv - mean * mean;
         if (var < 0.0) var = 0.0;
-        const double is = 1.0 / sqrt(var + (double)gs.eps);
+        const double is = inv_sqrt_f64(var + (double)gs.eps);
         const double c1 = gs.gstats[c] * n_inv;
         const double c2 = is * gs.gstats[gs.C + c] * n_inv;
         a = (float)is;

@@ -67,6 +67,7 @@ if __name__ == "__main__":
                 if all(v < 0 for v in vals):
                     break
                 print("  stage#%d %s" % (i, ["%.1f" % v for v in vals]))
+        print("prologue: kernel start %.2f, after griddep_wait %.2f, coefficients ready %.2f" % (t[296], t[297], t[298]))
         print("transformer stage 4 detail: x landed %.2f | per chunk [start, a_free ok, stores done, fenced+arrived]" % t[299])
         for c in range(3):
             print("  chunk %d %s" % (c, ["%.2f" % v for v in t[300 + 4 * c: 304 + 4 * c]]))
