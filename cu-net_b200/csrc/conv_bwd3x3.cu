@@ -38,10 +38,10 @@ constexpr int B3_X_OFF = B3_A_OFF + 2 * B3_SUB;     // raw x / outgoing G, doubl
 constexpr int B3_GT_BYTES = 12544;                  // >= (64 + 2*(64 + 1)) rows x 64 B
 constexpr int B3_G_OFF = B3_X_OFF + 2 * 16384;      // landed G / T with halo, double buffered: [buf][G | T]
 constexpr int B3_TAIL_OFF = B3_G_OFF + 4 * B3_GT_BYTES;
-constexpr int B3_COEF_OFF = B3_X_OFF;               // BnSmem + GradSmem live in the x buffers during the prologue only
+constexpr int B3_COEF_OFF = B3_A_OFF;               // BnSmem + GradSmem live in the activation-operand area during the prologue only
 constexpr int B3_STG_FLOATS = 32 * 128 * 9;         // dW staging in destination order [32 co][128 ci][9 taps]
 constexpr uint32_t B3_D1_COL = 320;                 // TMEM: D2 in columns [0, 320), D1 buffers at 320 and 384
-static_assert(sizeof(BnSmem) <= 8192 && sizeof(GradSmem) <= 8192, "coefficient overlay");
+static_assert(sizeof(BnSmem) <= 8192 && 8192 + sizeof(GradSmem) <= 2 * B3_SUB, "coefficient overlay");
 static_assert(B3_STG_FLOATS * 4 <= B3_TAIL_OFF, "dW staging must fit the (dead) weight / operand / landing regions");
 
 struct B3Tail {
@@ -121,18 +121,23 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
     for (int i = tid; i < 5 * B3_SUB / 16; i += B3_THREADS) sts128(b0 + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
     fence_proxy_async();
   }
+  __syncthreads();   // barrier inits / zero fill visible to every warp; still under the previous kernel
   griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
   griddep_launch();
+  // warp 0 (landing producer) needs no coefficient: it starts its copies at once; the other warps compute them in the
+  // activation-operand area (not in the x landing buffers) behind named barriers that do not include warp 0
   BnSmem* bn = reinterpret_cast<BnSmem*>(smem + B3_COEF_OFF);
   GradSmem* gc = reinterpret_cast<GradSmem*>(smem + B3_COEF_OFF + 8192);
-  compute_bn_coefs(p.in, bn, 128, tid, B3_THREADS);
-  compute_grad_coefs(p.dy, gc, tid, B3_THREADS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tail->tmem_base;
+  if (warp > 0) {
+    compute_bn_coefs(p.in, bn, 128, tid - 32, B3_THREADS - 32);
+    compute_grad_coefs(p.dy, gc, tid - 32, B3_THREADS - 32);
+    tc_fence_before();
+    b3_named_bar(1, B3_THREADS - 32);
+    tc_fence_after();
+  }
+  const uint32_t tmem = warp > 0 ? tail->tmem_base : 0u;
 
-  // per-role coefficients go to registers; after the next barrier the coefficient area is the x landing buffer
+  // per-role coefficients go to registers; after the next barrier the coefficient area is the activation operand
   const bool is_tr = warp >= 4 && warp < 12, is_ep = warp >= 12;
   const int t = tid - 128;                 // transformer thread index (0..255)
   const int c4 = t & 3, rI = t >> 2;       // im2col: 16-byte column (8 output channels) x pixel row rI
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
     is = bn->istd[k];
     nmi = -bn->mean[k] * is;  // xhat = x * istd - mean * istd
   }
-  __syncthreads();
+  if (warp > 0) b3_named_bar(1, B3_THREADS - 32);   // the coefficient area becomes the activation operand again
 
   if (warp == 0) {
     // ============================================================== landing producer

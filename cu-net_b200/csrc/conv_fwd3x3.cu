@@ -90,13 +90,18 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tail->tmem_base, 256);
+  __syncthreads();   // barrier inits visible to every warp; still under the previous kernel (before griddepcontrol.wait)
   griddep_wait();    // everything above overlaps the tail of the previous kernel (programmatic dependent launch)
   griddep_launch();
-  compute_bn_coefs(p.in, &tail->bn, 128, tid, F3_THREADS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tail->tmem_base;
+  // warp 0 (landing producer) needs no BatchNorm coefficient: it starts its copies at once, the other warps compute
+  // the coefficients behind a named barrier that does not include it (round 2, as in conv_fwd_v3 / conv_bwd1x1)
+  if (warp > 0) {
+    compute_bn_coefs(p.in, &tail->bn, 128, tid - 32, F3_THREADS - 32);
+    tc_fence_before();
+    f3_named_bar(2, F3_THREADS - 32);
+    tc_fence_after();
+  }
+  const uint32_t tmem = warp > 0 ? tail->tmem_base : 0u;
 
   if (warp == 0) {
     // ============================================================== landing producer
