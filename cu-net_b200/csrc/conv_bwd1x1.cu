@@ -40,6 +40,7 @@ constexpr int F1_THREADS = 1024;
 constexpr int F1_TRW = 12;      // transformer warps
 constexpr int F1_R = 64;         // pixels per stage
 constexpr int F1_SUB = F1_R * 128;  // one operand sub-tile: 64 rows x 128 B
+constexpr int F1_DWSTG = 16 * 32 * 144;  // final epilogue: one [32 co][32 k] fp32 tile (144-byte pitch) per epilogue warp
 constexpr int F1_GT_BYTES = 32768;  // one G/T landing set: G at +0, T at +16384, pool argmax bytes at +24576
 constexpr int F1_MAXCH = 3;      // 128-channel chunks (Cin <= 384)
 
@@ -566,6 +567,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         tc_commit(&tail->dt_free[db]);
       }
       tc_commit(&tail->done);
+      CUNET_TRACE_MARK(trace, 232);
     }
   } else if (is_tr) {
     // ============================================================== transformers (256 threads)
@@ -812,49 +814,76 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       if (tid == 128 + 32 * F1_TRW && i < 12) CUNET_TRACE_MARK(trace, 146 + 4 * i);
     }
     if (ns > 0) {
+      if (tid == 128 + 32 * F1_TRW) CUNET_TRACE_MARK(trace, 228);
+      // ---- per-channel sums.  The four pixel quarters of a channel meet in shared memory (the landed G/T set is dead
+      // once the last stage's D1 has been read), then ONE thread per concat channel adds to the global sums: the
+      // (dbeta, dgamma, gstats) arrays are a few dozen cache lines, and 16 warps x 3 chunks x 4 atomics per CTA queued
+      // on their L2 slices for 7-10 us per launch (in-kernel timeline, round 2) -- a quarter of that now.
+      {
+        // (placed behind the dW staging tiles of the warps that are already past this point: see below)
+        float2* red = reinterpret_cast<float2*>(smem + max(L.gt_off, F1_DWSTG));
 #pragma unroll
-      for (int c = 0; c < F1_MAXCH; ++c) {
-        const int kg = c * 128 + k;
-        if (c >= nchunk || kg >= Cin) continue;
-        int ps = 0;
-        while (kg >= tail->seg_start[ps + 1]) ++ps;
-        const int kl = kg - tail->seg_start[ps], Cp = p.in.seg[ps].C;
-        // dgamma = sum dz*xhat = istd * (sum dz*x - mean * sum dz); mean / istd of the channel as compute_bn_coefs has them
-        const cunet_seg& sg = p.in.seg[ps];
-        const double mean = sg.stats[kl] * sg.inv_count;
-        double var = sg.stats[Cp + kl] * sg.inv_count - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float is = (float)inv_sqrt_f64(var + (double)p.in.eps);
-        const float dg = is * (a_dx[c] - (float)mean * a_db[c]);
-        const float gm = tail->ech[kg].z;
-        atomicAdd(p.dbeta + kg, a_db[c]);
-        atomicAdd(p.dgamma + kg, dg);
-        if (p.gacc[ps].gstats) {
-          // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma)  (see conv_dgrad_v2.cu)
-          atomicAdd(p.gacc[ps].gstats + kl, (double)(gm * a_db[c]));
-          atomicAdd(p.gacc[ps].gstats + Cp + kl, (double)(gm * dg));
+        for (int c = 0; c < F1_MAXCH; ++c)
+          if (c < nchunk) red[pq * MAX_CIN + c * 128 + k] = make_float2(a_db[c], a_dx[c]);
+        f1_named_bar(2, F1_THREADS - 128 - 32 * F1_TRW);
+        const int kg = tid - (128 + 32 * F1_TRW);
+        if (kg < Cin) {
+          const float2 r0 = red[kg], r1 = red[MAX_CIN + kg], r2 = red[2 * MAX_CIN + kg], r3 = red[3 * MAX_CIN + kg];
+          const float s_db = (r0.x + r1.x) + (r2.x + r3.x), s_dx = (r0.y + r1.y) + (r2.y + r3.y);
+          int ps = 0;
+          while (kg >= tail->seg_start[ps + 1]) ++ps;
+          const int kl = kg - tail->seg_start[ps], Cp = p.in.seg[ps].C;
+          // dgamma = sum dz*xhat = istd * (sum dz*x - mean * sum dz); mean / istd of the channel as compute_bn_coefs has them
+          const cunet_seg& sg = p.in.seg[ps];
+          const double mean = sg.stats[kl] * sg.inv_count;
+          double var = sg.stats[Cp + kl] * sg.inv_count - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float is = (float)inv_sqrt_f64(var + (double)p.in.eps);
+          const float dg = is * (s_dx - (float)mean * s_db);
+          const float gm = tail->ech[kg].z;
+          atomicAdd(p.dbeta + kg, s_db);
+          atomicAdd(p.dgamma + kg, dg);
+          if (p.gacc[ps].gstats) {
+            // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma)  (see conv_dgrad_v2.cu)
+            atomicAdd(p.gacc[ps].gstats + kl, (double)(gm * s_db));
+            atomicAdd(p.gacc[ps].gstats + Cp + kl, (double)(gm * dg));
+          }
         }
       }
       // ---- weight gradient: D2_c[co][k] -> dW[co][k]: lane = output channel, 32 consecutive k per thread and chunk
+      if (tid == 128 + 32 * F1_TRW) CUNET_TRACE_MARK(trace, 229);
       mbar_wait(&tail->done, 0);
       tc_fence_after();
       if (tid == 128 + 32 * F1_TRW) CUNET_TRACE_MARK(trace, 230);
-      const int co = k;                      // TMEM lane
+      // Every warp owns a [32 co][32 k] block per chunk.  Out of TMEM a lane holds one co (row of dW) -- reductions issued
+      // like that touch 32 half-used sectors per instruction, and the L2 retires reductions per sector (one-stage
+      // launch: 5.2 us for 15 MB).  The block is turned in a private shared-memory tile (weights are dead after
+      // `done`; 144-byte pitch: conflict-free both ways) so that 8 lanes cover one full 128-byte line of a dW row.
+      const uint32_t stg = smem_u32(smem + L.w_off) + (uint32_t)(warp - 4 - F1_TRW) * (32u * 144u);   // 16 tiles = F1_DWSTG bytes
+      const int co0 = qd * 32, rsub = lane >> 3, c16 = lane & 7;
       for (int c = 0; c < nchunk; ++c) {
         const int kvalid = min(min(128, Cin - c * 128), L.dwc - c * 128);   // real input channels of this chunk
         const int col0 = 32 * pq;
         if (col0 >= kvalid) continue;
         float v[32];
-        f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)(qd * 32) << 16) + (uint32_t)col0, v);
-        if (col0 + 16 < kvalid)
-          f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)(qd * 32) << 16) + (uint32_t)(col0 + 16), v + 16);
+        f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)co0 << 16) + (uint32_t)col0, v);
+        f1_tmem_ld16_nowait(tmem + (uint32_t)c * 128u + ((uint32_t)co0 << 16) + (uint32_t)(col0 + 16), v + 16);
         f1_tmem_wait_ld();
-        if (co < p.Cout) {
-          float* dst = L.dw + (long)co * L.dwc + c * 128 + col0;
 #pragma unroll
-          for (int q = 0; q < 32; q += 4)
-            if (col0 + q < kvalid) f1_red_add_v4(dst + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
+        for (int q = 0; q < 32; q += 4)
+          sts128(stg + (uint32_t)lane * 144u + (uint32_t)q * 4u,
+                 make_uint4(__float_as_uint(v[q]), __float_as_uint(v[q + 1]), __float_as_uint(v[q + 2]), __float_as_uint(v[q + 3])));
+        __syncwarp();
+        const bool kok = col0 + c16 * 4 < kvalid;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int row = r * 4 + rsub;
+          const uint4 u = f1_lds128(stg + (uint32_t)row * 144u + (uint32_t)c16 * 16u);
+          if (kok && co0 + row < p.Cout)
+            f1_red_add_v4(L.dw + (long)(co0 + row) * L.dwc + c * 128 + col0 + c16 * 4, __uint_as_float(u.x),
+                          __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
         }
+        __syncwarp();
       }
       if (tid == 128 + 32 * F1_TRW) CUNET_TRACE_MARK(trace, 231);
     }

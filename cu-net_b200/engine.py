@@ -430,9 +430,10 @@ class Engine(object):
             rc = self._launch(fn, prm, st_main)
             if rc != 0:
                 L.check(rc, fn.__name__)
-        ev = self._evpool[-1]
-        ev.record(side)
-        main.wait_event(ev)
+        if k:   # join the side branch (nothing to join when every backward-filter is fused into its backward-data)
+            ev = self._evpool[-1]
+            ev.record(side)
+            main.wait_event(ev)
 
     def optimizer_step(self, alpha=0.99, eps=1e-8, start=0, end=None, grads=None):
         """RMSprop on elements [start, end) of the flat buffers; ``grads`` (default: the same slice of the gradient

@@ -108,7 +108,8 @@ def trace(name):
     show("mma", 96, 3, ["dT ready", "first D1 issued", "stage issued"])
     show("epilogue", 144, 4, ["chunk0 acc full", "chunk0 done", "stage done"])
     show("store", 200, 2, ["stores read"])
-    print("  dW epilogue %.1f -> %.1f" % (t[230], t[231]))
+    print("  tail: stages done %.1f, channel sums added %.1f, wgrad MMAs committed %.1f, D2 complete %.1f, dW added %.1f"
+          % (t[228], t[229], t[232], t[230], t[231]))
 
 
 if __name__ == "__main__":
