@@ -48,6 +48,7 @@ struct B3Tail {
   uint64_t w_full, ops_ready, ops_free, done, stores_done;
   uint64_t gt_full[2], gt_free[2], x_full[2], x_free[2], d1_full[2], d1_free[2], g_ready[2];
   uint32_t tmem_base;
+  float2 csum[128];          // final epilogue: (dbeta, dgamma) partial of the second pixel half
 };
 
 __device__ __forceinline__ void b3_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
@@ -348,13 +349,22 @@ __global__ void __launch_bounds__(B3_THREADS, 1) conv_bwd3x3_kernel(const __grid
         mbar_arrive(&tail->d1_free[b]);
       }
     }
-    if (ns > 0) {
-      atomicAdd(p.dbeta + k, a_db);
-      atomicAdd(p.dgamma + k, a_dg);
-      if (p.gacc[0].gstats) {
-        // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma)  (see conv_dgrad_v2.cu)
-        atomicAdd(p.gacc[0].gstats + k, (double)(gm * a_db));
-        atomicAdd(p.gacc[0].gstats + 128 + k, (double)(gm * a_dg));
+    {
+      // the two pixel halves of a channel meet in shared memory: one thread per channel and CTA adds to the global sums
+      // (same-line atomics queue on a few L2 slices -- conv_bwd1x1.cu's tail lost 9 us per launch to that)
+      if (hf) tail->csum[k] = make_float2(a_db, a_dg);
+      b3_named_bar(2, 256);
+      if (!hf && ns > 0) {
+        const float2 o = tail->csum[k];
+        a_db += o.x;
+        a_dg += o.y;
+        atomicAdd(p.dbeta + k, a_db);
+        atomicAdd(p.dgamma + k, a_dg);
+        if (p.gacc[0].gstats) {
+          // this consumer's share of (sum G, sum G*xhat) = gamma * (dbeta, dgamma)  (see conv_dgrad_v2.cu)
+          atomicAdd(p.gacc[0].gstats + k, (double)(gm * a_db));
+          atomicAdd(p.gacc[0].gstats + 128 + k, (double)(gm * a_dg));
+        }
       }
     }
     // ---- weight gradient: D2[128 ci][(tap, co)] -> dW[co][ci][tap].  A thread owns one ci (TMEM lane), but the

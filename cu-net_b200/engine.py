@@ -52,9 +52,12 @@ class Engine(object):
         self.tdtype = torch.bfloat16 if self.dtype == L.BF16 else torch.float32
         self.double_bn_update = double_bn_update
         self.grad_scale = 1.0          # 1 / world_size under data parallelism
-        # pixel rows from which a 1x1 conv's backward runs as ONE fused dgrad+wgrad launch (CUNET_BWD1X1_MIN_ROWS)
+        # pixel rows from which a 1x1 conv's backward runs as ONE fused dgrad+wgrad launch (CUNET_BWD1X1_MIN_ROWS).
+        # Default: always -- since the fused kernel's tail was fixed (channel sums through shared memory, full-line dW
+        # reductions) it beats dgrad || wgrad on two streams at every size (16x16 batch 24: 17.7 us against ~21 us;
+        # whole CU-Net-8 step 12.32 ms with the old 12288-row threshold, 12.00 ms with 0)
         import os
-        self.fuse1x1_min_rows = int(os.environ.get("CUNET_BWD1X1_MIN_ROWS", "12288"))
+        self.fuse1x1_min_rows = int(os.environ.get("CUNET_BWD1X1_MIN_ROWS", "0"))
         if os.environ.get("CUNET_BWD1X1_OFF"):
             self.fuse1x1_min_rows = 1 << 62
         self.wgrad_serial = os.environ.get("CUNET_WGRAD_SIDE", "1") == "0"   # debug: no side stream
@@ -314,9 +317,9 @@ class Engine(object):
                 # one fused launch on the main stream (csrc/conv_bwd3x3.cu)
                 calls.append((lib.cunet_conv_bwd3x3, (dp, wp)))
             elif self.is_fused_1x1(op):
-                # large 1x1: backward-data and backward-filter share the gradient operand and the landed sources ->
-                # one fused launch (csrc/conv_bwd1x1.cu).  Small maps stay split: there a launch is pure latency and
-                # the backward-filter hides on the side stream behind the backward-data chain.
+                # 1x1: backward-data and backward-filter share the gradient operand and the landed sources ->
+                # one fused launch (csrc/conv_bwd1x1.cu); the split form below remains for fp32 and for shapes the
+                # fused kernel does not take (it falls back by itself) and for A/B runs (CUNET_BWD1X1_MIN_ROWS)
                 calls.append((lib.cunet_conv_bwd1x1, (dp, wp)))
             else:
                 calls.append((lib.cunet_conv_dgrad, dp))
