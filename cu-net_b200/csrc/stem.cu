@@ -9,9 +9,25 @@ namespace cunet {
 constexpr int STEM_K = 147;      // 3 * 7 * 7
 constexpr int STEM_KPAD = 160;
 
+// K index -> (input offset relative to the window's centre row/column, dy, dx), built once per block: the first version
+// decomposed k with two integer divisions per ELEMENT (186 us per step at batch 24 for a 126 MB matrix).
 template <typename T>
-__global__ void stem_im2col_kernel(const float* __restrict__ img, T* __restrict__ cols, int N, int Hi, int Wi) {
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, T* __restrict__ cols, int N,
+                                                          int Hi, int Wi) {
   using E = Elem<T>;
+  __shared__ int tab_off[STEM_KPAD];
+  __shared__ int tab_yx[STEM_KPAD];   // (dy + 3) << 8 | (dx + 3), or -1 for the padding columns
+  for (int k = threadIdx.x; k < STEM_KPAD; k += blockDim.x) {
+    if (k < STEM_K) {
+      const int c = k / 49, r = k - c * 49, kh = r / 7, kw = r - kh * 7;
+      tab_off[k] = (c * Hi + kh - 3) * Wi + kw - 3;
+      tab_yx[k] = (kh << 8) | kw;
+    } else {
+      tab_off[k] = 0;
+      tab_yx[k] = -1;
+    }
+  }
+  __syncthreads();
   const int Ho = Hi >> 1, Wo = Wi >> 1;
   constexpr int CPR = STEM_KPAD / E::EPC;
   const long total = (long)N * Ho * Wo * CPR;
@@ -21,16 +37,15 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, T* __restrict_
     const int ox = (int)(px % Wo);
     const long t = px / Wo;
     const int oy = (int)(t % Ho), n = (int)(t / Ho);
+    const float* base = img + ((long)n * 3 * Hi + 2 * oy) * Wi + 2 * ox;
     float f[E::EPC];
 #pragma unroll
     for (int e = 0; e < E::EPC; ++e) {
       const int k = j * E::EPC + e;
+      const int yx = tab_yx[k];
+      const int iy = 2 * oy + (yx >> 8) - 3, ix = 2 * ox + (yx & 255) - 3;
       float v = 0.f;
-      if (k < STEM_K) {
-        const int c = k / 49, r = k - c * 49, kh = r / 7, kw = r - kh * 7;
-        const int iy = 2 * oy + kh - 3, ix = 2 * ox + kw - 3;
-        if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = img[(((long)n * 3 + c) * Hi + iy) * Wi + ix];
-      }
+      if (yx >= 0 && (unsigned)iy < (unsigned)Hi && (unsigned)ix < (unsigned)Wi) v = base[tab_off[k]];
       f[e] = v;
     }
     *reinterpret_cast<uint4*>(reinterpret_cast<char*>(cols) + i * 16) = Chunk<T>::pack(f);
