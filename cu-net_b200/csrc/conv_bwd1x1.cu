@@ -574,8 +574,15 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
     const bool gcol_ok = cc * 8 < p.dy.C;
     const bool gcol_used = cc * 8 < L.npad;
     const uint32_t dtb0 = smem_u32(smem + L.dt_off), ab = smem_u32(smem + L.a_off);
-    const int* lowmap = tail->lowmap;
-    const int* rowpos = tail->rowpos;
+    // this thread's rows are the same in every stage: their half-resolution row / 2x2 position are registers, not a
+    // dependent shared-memory load in front of every operand load
+    int lowr[3], rpos[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int r = min(rb + 24 * q, F1_R - 1);
+      lowr[q] = tail->lowmap[r];
+      rpos[q] = tail->rowpos[r];
+    }
     GradCoef<bf16> gcf;
     {
       const int co2 = ((cc * 8) & 127) >> 1;
@@ -612,14 +619,14 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
           uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
           if (gcol_ok && r < nv) {
             GradRaw<bf16> raw;
-            const int loc = p.dy.pooled ? lowmap[r] : r;
+            const int loc = p.dy.pooled ? lowr[q] : r;
             raw.g = f1_lds128(rg + (uint32_t)(loc * ldo));
             if (p.dy.mode == 1) raw.t = f1_lds128(rg + 16384u + (uint32_t)(loc * ldo));
             if (p.dy.pooled) {
               const uint2 iv = f1_lds64(ri + (uint32_t)(loc * p.dy.C));
               raw.idx[0] = iv.x;
               raw.idx[1] = iv.y;
-              raw.pos = (uint32_t)rowpos[r] + posadd;
+              raw.pos = (uint32_t)rpos[q] + posadd;
             }
             o = gcf.apply(p.dy, raw, lo_unused);
           }
@@ -663,7 +670,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         for (int q = 0; q < 3; ++q) {
           const int r = rb + 24 * q;
           raw[q] = make_uint4(0, 0, 0, 0);
-          if (cvalid && r < nv) raw[q] = f1_lds128(rx + ((uint32_t)(cup ? lowmap[r] : r) << lsh));
+          if (cvalid && r < nv) raw[q] = f1_lds128(rx + ((uint32_t)(cup ? lowr[q] : r) << lsh));
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {

@@ -341,7 +341,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
   } else if (is_tr) {
     // ============================================================== transformers (512 threads)
     const uint32_t ab = smem_u32(smem + L.a_off);
-    const int* lowmap = tail->lowmap;
+    int lowr[2];   // this thread's rows are the same in every stage: their half-resolution rows live in registers
+#pragma unroll
+    for (int q = 0; q < 2; ++q) lowr[q] = tail->lowmap[rb + 32 * q];
     // one packed word per chunk: bit 31 valid | bit 30 upsampled source | bits 16..17 log2(C/32) | bits 0..15 byte
     // offset of this thread's 16-byte column inside an x buffer
     uint32_t cs_pk[F3_MAXCH];
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd_v3_kernel(const __grid
           for (int q = 0; q < 2; ++q) {
             const int r = rb + 32 * q;
             raw[q] = make_uint4(0, 0, 0, 0);
-            if (cvalid && r < nv) raw[q] = f3_lds128(rx + ((uint32_t)(cup ? lowmap[r] : r) << lsh));
+            if (cvalid && r < nv) raw[q] = f3_lds128(rx + ((uint32_t)(cup ? lowr[q] : r) << lsh));
           }
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
