@@ -298,7 +298,7 @@ extern "C" int cunet_conv_fwd(const cunet_conv_fwd_params* p, void* stream) {
     if (r != 0) return r < 0 ? r : 0;
   }
   if (p->taps == 9) {
-    // bf16 dense-layer 3x3 (128 -> 32, W in {8..64}): persistent shifted-descriptor kernel; everything else: this file
+    // bf16 dense-layer 3x3 (128 -> 32, W in {2..64}): persistent shifted-descriptor kernel; everything else: this file
     const int r = cunet_conv_fwd3x3_try(p, reinterpret_cast<cudaStream_t>(stream));
     if (r != 0) return r < 0 ? r : 0;
   }

@@ -48,15 +48,18 @@ __device__ __forceinline__ uint4 f3_lds128(uint32_t saddr) {
 __device__ __forceinline__ void f3_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // padded raster: position -> (image, padded row hp in [0, H+2), w); real pixel iff 1 <= hp <= H
+// Maps narrower than 8 pixels (the 4x4 neck of the hourglass) use a raster of width 8 whose columns >= Wr are padding
+// like the rows above and below an image: a shift by one raster row then stays a multiple of the swizzle period.
 struct F3Geom {
-  int H, W, lw, S, P;  // S = (H + 2) * W positions per image, P = N * S
+  int H, W, lw, S, P;  // W = raster width (>= 8), S = (H + 2) * W positions per image, P = N * S
+  int Wr, lwr;         // real width of the map and its log2
   __device__ __forceinline__ bool real(int pos, int& grow, int& w) const {
     w = pos & (W - 1);
     if (pos < 0 || pos >= P) return false;
     const int img = pos / S;
     const int hp = (pos - img * S) >> lw;
-    grow = ((img * H + hp - 1) << lw) + w;
-    return hp >= 1 && hp <= H;
+    grow = ((img * H + hp - 1) << lwr) + w;
+    return hp >= 1 && hp <= H && w < Wr;
   }
 };
 
@@ -72,8 +75,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
   F3Tail* tail = reinterpret_cast<F3Tail*>(smem + F3_TAIL_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   F3Geom g;
-  g.H = p.H; g.W = p.W; g.lw = 31 - __clz(p.W); g.S = (p.H + 2) * p.W; g.P = p.N * g.S;
-  const int W = p.W;
+  const int W = max(p.W, 8), Wr = p.W;   // raster width, real width
+  g.H = p.H; g.W = W; g.lw = 31 - __clz(W); g.S = (p.H + 2) * W; g.P = p.N * g.S;
+  g.Wr = Wr; g.lwr = 31 - __clz(Wr);
   const int tile0 = (int)blockIdx.x, tstride = (int)gridDim.x;
   CUNET_TRACE_LOAD(trace, g_f3_trace)
 
@@ -120,6 +124,26 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
       for (int tile = tile0; tile < ntiles; tile += tstride, ++i) {
         const int p0w = tile * 128 - W;  // position of window row 0
         const int ws = max(0, p0w), we = min(g.P, tile * 128 + 128 + W);
+        if (Wr < W) {
+          // narrow map: one copy per real image row of the window (window bounds are multiples of the raster width)
+          const int r0 = ws >> g.lw, r1 = we >> g.lw;
+          uint32_t nreal = 0;
+          for (int rr = r0; rr < r1; ++rr) {
+            const int hp = rr % (p.H + 2);
+            nreal += (hp >= 1 && hp <= p.H) ? 1u : 0u;
+          }
+          mbar_wait(&tail->raw_free, (i & 1u) ^ 1u);
+          if (i < 16) CUNET_TRACE_MARK(trace, 0 + i);
+          if (nreal) mbar_arrive_expect_tx(&tail->raw_full, nreal * (uint32_t)Wr * 256u);
+          else mbar_arrive(&tail->raw_full);
+          for (int rr = r0; rr < r1; ++rr) {
+            const int img = rr / (p.H + 2), hp = rr - img * (p.H + 2);
+            if (hp >= 1 && hp <= p.H)
+              bulk_g2s(smem + F3_RAW_OFF + (rr * W - p0w) * 256, xsrc + ((long)(img * p.H + hp - 1) * Wr) * 256,
+                       (uint32_t)Wr * 256u, &tail->raw_full);
+          }
+          continue;
+        }
         const int i0 = ws / g.S, i1 = (we - 1) / g.S;
         uint32_t total = 0;
         for (int img = i0; img <= i1; ++img) {
@@ -238,7 +262,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
         for (int j = 0; j < 32; ++j) xc[qd][1][j] = yp[j];
       }
       f3_named_bar(2, 128);
-      const bool take_l = valid && w > 0, take_r = valid && w < W - 1;
+      const bool take_l = valid && w > 0, take_r = valid && w < Wr - 1;
       float o[32];
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
@@ -250,7 +274,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) conv_fwd3x3_kernel(const __grid
           float up = __shfl_up_sync(0xffffffffu, ym[c], 1);
           float dn = __shfl_down_sync(0xffffffffu, yp[c], 1);
           if (lane == 0) up = qd > 0 ? xc[qd - 1][0][c] : 0.f;     // row 0 of a tile has w == 0: masked anyway
-          if (lane == 31) dn = qd < 3 ? xc[qd + 1][1][c] : 0.f;    // row 127 has w == W - 1
+          if (lane == 31) dn = qd < 3 ? xc[qd + 1][1][c] : 0.f;    // row 127 is the last raster column: masked anyway
           o[c] = y0[j] + (take_l ? up : 0.f) + (take_r ? dn : 0.f);
         }
       }
@@ -322,8 +346,8 @@ int cunet_conv_fwd3x3_try(const cunet_conv_fwd_params* p, cudaStream_t st) {
   const cunet_seg& sg = p->in.seg[0];
   if (sg.C != 128 || sg.ld != 128 || sg.up) return 0;
   const int W = p->W, H = p->H;
-  if ((W & (W - 1)) || W < 8 || W > 64 || H < 1) return 0;
-  const long P = (long)p->N * (H + 2) * W;
+  if ((W & (W - 1)) || W < 2 || W > 64 || H < 1) return 0;
+  const long P = (long)p->N * (H + 2) * (W < 8 ? 8 : W);   // narrow maps: raster of width 8 (F3Geom)
   if (P <= 0) return 1;
   if (P > (1L << 30)) return 0;
   const int ntiles = (int)((P + 127) / 128);

@@ -105,6 +105,10 @@ CASES = [
     ("1x1_pool_tail", 3, 4, 4, [128, 32, 32], [0, 0, 0], 128, 1, True, True, False, None),
     ("1x1_big", 4, 64, 64, [128, 32, 32], [0, 0, 0], 128, 1, False, True, False, None),
     # dense-layer 3x3, persistent shifted-descriptor kernel in bf16 (conv_fwd3x3.cu): every resolution of the network
+    ("3x3_4x4_b24", 24, 4, 4, [128], [0], 32, 9, False, True, False, None),      # the neck: raster of width 8
+    ("3x3_4x4_b5_eval", 5, 4, 4, [128], [0], 32, 9, False, False, False, None),
+    ("3x3_2x2", 7, 2, 2, [128], [0], 32, 9, False, True, False, None),
+    ("3x3_rect_4w", 3, 8, 4, [128], [0], 32, 9, False, True, False, None),
     ("3x3_8x8", 3, 8, 8, [128], [0], 32, 9, False, True, False, None),
     ("3x3_8x8_b24", 24, 8, 8, [128], [0], 32, 9, False, True, False, None),
     ("3x3_32x32", 5, 32, 32, [128], [0], 32, 9, False, True, False, None),
@@ -218,6 +222,7 @@ QUANT_CASES = [
     ("3x3_q8", 2, 16, 16, [128], [0], 32, 9, 8, False, None),
     ("3x3_q8_b24", 24, 64, 64, [128], [0], 32, 9, 8, False, None),
     ("3x3_q4", 3, 8, 8, [128], [0], 32, 9, 4, False, None),
+    ("3x3_q6_4x4", 24, 4, 4, [128], [0], 32, 9, 6, False, None),
     ("head68_q8", 2, 16, 16, [128], [0], 68, 1, 8, True, 80),
     ("head68_q8_b24", 24, 64, 64, [128], [0], 68, 1, 8, True, 80),
     ("head16_q8_b24", 24, 64, 64, [128], [0], 16, 1, 8, True, 16),

@@ -13,7 +13,7 @@ for c in cunet8 cunet2 cunet8bin cunet16; do
 done
 timeout 400 python bench.py --impl reference --steps 3 --warmup 3 > $O/bench_cunet8_reference.json 2> $O/bench_ref.err; echo "ref rc=$?" >> $O/rc.log
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(conv_|stem_|mse_|decode_|pack_|rmsprop|bn_|quant_)' \
-   --launch-skip ${SKIP:-1300} --launch-count ${COUNT:-640} --csv --log-file $O/launches_cunet8_eager.csv \
+   --launch-skip ${SKIP:-1200} --launch-count ${COUNT:-1300} --csv --log-file $O/launches_cunet8_eager.csv \
    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-loss-check > $O/launches_run.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:conv_bwd1x1 --launch-skip 4 --launch-count 1 -f \
    -o $O/ncu_r2_bwd1x1_320up64 python tools/time_bwd1x1.py 320up64 > $O/ncu_bwd1x1.log 2>&1
