@@ -559,7 +559,7 @@ static long g_fwd_v3_min_rows = [] {
 int cunet_conv_fwd_v3_try(const cunet_conv_fwd_params* p, cudaStream_t st) {
   if (g_fwd_v3_min_rows < 0) return 0;
   if (p->dtype != CUNET_BF16 || p->taps != 1) return 0;
-  if (p->in.bn_train != 0 && p->in.bn_train != 1) return 0;   // identity (im2col) input of the stem: generic kernel
+  if (p->in.bn_train < 0 || p->in.bn_train > 2) return 0;     // 2: identity input (the stem's im2col blocks)
   if (p->CoutPad % 16 || p->CoutPad < 16 || p->CoutPad > 128) return 0;
   if (p->out_fp32) {
     if (p->pool || p->out_ld % 4 || p->out_ld > p->CoutPad) return 0;

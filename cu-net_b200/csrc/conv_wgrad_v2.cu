@@ -326,7 +326,6 @@ CUNET_TRACE_SETTER(cunet_debug_trace_wgrad_v2, g_w2_trace)
 int cunet_conv_wgrad_v2_try(const cunet_conv_wgrad_params* p, cudaStream_t st) {
   if (p->dtype != CUNET_BF16 || p->taps != 1) return 0;
   if (p->dy.ld != p->dy.C || p->dy.C > 128 || (p->dy.C & 7) || p->Cout > 128) return 0;
-  if (p->in.bn_train == 2) return 0;   // identity (im2col) input of the stem: generic kernel
   int cin = 0, low = p->dy.pooled;
   for (int s = 0; s < p->in.nseg; ++s) {
     const cunet_seg& sg = p->in.seg[s];

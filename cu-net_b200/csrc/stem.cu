@@ -48,7 +48,12 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
       if (yx >= 0 && (unsigned)iy < (unsigned)Hi && (unsigned)ix < (unsigned)Wi) v = base[tab_off[k]];
       f[e] = v;
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(cols) + i * 16) = Chunk<T>::pack(f);
+    // two column blocks, each a dense matrix: [px][128] followed by [px][32] -- the concat-segment widths the
+    // persistent conv kernels take (a 160-wide row would straddle their 128-channel chunks)
+    constexpr int C0V = 128 / E::EPC;   // 16-byte vectors per row of block 0
+    const long npx = (long)N * Ho * Wo;
+    const long vec = j < C0V ? px * C0V + j : npx * C0V + px * (CPR - C0V) + (j - C0V);
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(cols) + vec * 16) = Chunk<T>::pack(f);
   }
 }
 

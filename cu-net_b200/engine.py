@@ -213,12 +213,8 @@ class Engine(object):
             calls = []
             # stem
             sp = L.ConvFwdParams()
-            sp.inp.nseg = 1
-            sp.inp.seg[0].ptr = self.cols.data_ptr()
-            sp.inp.seg[0].C, sp.inp.seg[0].ld, sp.inp.seg[0].up = 160, 160, 0
-            sp.inp.seg[0].inv_count = 1.0
-            sp.inp.bn_train = 2
-            sp.N, sp.H, sp.W, sp.taps = N, p.stem_res, p.stem_res, 1
+            self._stem_cols(sp.inp)
+            sp.N, sp.H, sp.W, sp.taps = self._stem_geom()
             sp.wpack, sp.Cout, sp.CoutPad = self.wfwd["features.conv0"], p.C0, p.C0
             sp.out, sp.out_ld, sp.out_fp32 = self.act["stem.y"].data_ptr(), p.C0, 0
             sp.out_stats = self._stats("stem.y") if mode else None
@@ -339,19 +335,36 @@ class Engine(object):
             sb.N, sb.H, sb.W, sb.eps, sb.dtype, sb.phase = N, p.stem_res, p.stem_res, BN_EPS, self.dtype, phase
             calls.append((lib.cunet_stem_bwd, sb))
         wp = L.ConvWgradParams()
-        wp.inp.nseg = 1
-        wp.inp.seg[0].ptr, wp.inp.seg[0].C, wp.inp.seg[0].ld = self.cols.data_ptr(), 160, 160
-        wp.inp.seg[0].inv_count = 1.0
-        wp.inp.bn_train = 2
+        self._stem_cols(wp.inp)
         wp.dy.g, wp.dy.C, wp.dy.ld, wp.dy.mode, wp.dy.pooled = self.dy0.data_ptr(), p.C0, p.C0, 0, 0
         wp.dy.inv_count = 1.0
-        wp.N, wp.H, wp.W, wp.taps, wp.Cout = N, p.stem_res, p.stem_res, 1, p.C0
+        (wp.N, wp.H, wp.W, wp.taps), wp.Cout = self._stem_geom(), p.C0
         wp.dw, wp.nsplit, wp.dtype, wp.dw_cin = self._gp("features.conv0.weight"), 0, self.dtype, 147
         calls.append((lib.cunet_conv_wgrad, wp))
         self.bwd_calls = calls
         self.bwd_wgrad_calls = wcalls
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._evpool = [torch.cuda.Event() for _ in range(len(wcalls) + 1)]
+
+    def _stem_cols(self, cc):
+        """The im2col matrix as an identity-input concat of its two column blocks (cunet_stem_im2col's layout)."""
+        rows = self.N * self.plan.stem_res ** 2
+        esz = self.cols.element_size()
+        cc.nseg = 2
+        for i, (off, c) in enumerate(((0, 128), (rows * 128 * esz, 32))):
+            cc.seg[i].ptr = self.cols.data_ptr() + off
+            cc.seg[i].C, cc.seg[i].ld, cc.seg[i].up = c, c, 0
+            cc.seg[i].inv_count = 1.0
+        cc.bn_train = 2
+
+    def _stem_geom(self):
+        """(N, H, W, taps) of conv0 as a 1x1 conv over the im2col rows.  Only the row count matters to a 1x1 conv without
+        pooling or upsampling; maps wider than 64 are presented as more images of 64x64 so that the persistent kernels
+        (csrc/conv_fwd_v3.cu, csrc/conv_wgrad_v2.cu: W <= 64) take them."""
+        r = self.plan.stem_res
+        if r > 64 and r % 64 == 0:
+            return self.N * (r // 64) ** 2, 64, 64, 1
+        return self.N, r, r, 1
 
     # ------------------------------------------------------------------------------------------ execution
     def _run(self, calls):

@@ -172,10 +172,12 @@ int cunet_conv_bwd1x1(const cunet_conv_dgrad_params* d, const cunet_conv_wgrad_p
 
 /* ---- stem: conv0 7x7 s2 p3 -> norm0 -> relu0 -> pool0 (models/cu_net.py:299-304) ------------------
  * conv0 runs on the tensor cores through cunet_conv_fwd / cunet_conv_wgrad with an identity input
- * (bn_train == 2) over an im2col matrix [N*Ho*Wo][160] (147 = 3*7*7 columns in the reference's
- * weight-flattening order c*49 + kh*7 + kw, zero padded to 160). */
+ * (bn_train == 2) over an im2col matrix of 160 columns (147 = 3*7*7 in the reference's weight-flattening
+ * order c*49 + kh*7 + kw, zero padded to 160), stored as TWO dense column blocks -- columns 0..127 as
+ * [N*Ho*Wo][128], then columns 128..159 as [N*Ho*Wo][32] -- i.e. as two concat segments (C = ld = 128 and 32). */
 int cunet_stem_im2col(const float* img /* [N][3][Hi][Wi] fp32, NCHW as the reference feeds it */,
-                      void* cols /* [N*Ho*Wo][160] dtype */, int N, int Hi, int Wi, int dtype, void* stream);
+                      void* cols /* [N*Ho*Wo][128] ++ [N*Ho*Wo][32] dtype */, int N, int Hi, int Wi, int dtype,
+                      void* stream);
 
 /* norm0 -> relu0 -> pool0 forward: y [N*H*W][128] -> x [N*H/2*W/2][128], accumulating the statistics of x.
  * bn_train: 1 batch statistics from y_stats, 0 running statistics. */

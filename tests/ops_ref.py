@@ -45,7 +45,8 @@ def quan_act(a, bits):
     return torch.round(torch.clamp(a, -1 + 1 / s, 1 - 1 / s) * s) / s
 
 
-def conv_fwd_ref(srcs, ups, n, h, w, scale, shift, weight, pool=False, dtype=torch.float32, act_bits=0):
+def conv_fwd_ref(srcs, ups, n, h, w, scale, shift, weight, pool=False, dtype=torch.float32, act_bits=0,
+                 identity=False):
     """srcs: list of row tensors (at h,w or h/2,w/2 when up). Returns (out_rows, pool_idx or None)."""
     xs = []
     for s, up in zip(srcs, ups):
@@ -57,6 +58,8 @@ def conv_fwd_ref(srcs, ups, n, h, w, scale, shift, weight, pool=False, dtype=tor
         xs.append(x)
     x = torch.cat(xs, 1)
     a = F.relu(x * scale.to(dtype).view(1, -1, 1, 1) + shift.to(dtype).view(1, -1, 1, 1))
+    if identity:       # bn_train == 2: the stem's im2col operand, no BatchNorm and no ReLU in front of the conv
+        a = x
     if act_bits:
         a = quan_act(a, act_bits)
     y = F.conv2d(a, weight.to(dtype), padding=weight.shape[-1] // 2)

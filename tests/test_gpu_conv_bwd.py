@@ -372,3 +372,27 @@ def test_conv_bwd_quantized_activations(case, dtype_name):
     assert ew < tol, "%s %s dW rel err %g" % (name, dtype_name, ew)
     # and the quantizer matters: the unquantized reference is measurably different
     assert _relerr(outs0[0], outs[0]) > 3 * eg and _relerr(dw0.reshape(cout, 128, -1), dw_ref.reshape(cout, 128, -1)) > 3 * ew
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,h,w", [(3, 16, 16), (8, 64, 64), (96, 64, 64)])
+def test_conv_wgrad_identity_input(n, h, w):
+    """conv0's weight gradient over the im2col blocks (two dense column blocks of 128 and 32 channels, bn_train == 2: no
+    BatchNorm / ReLU in front), plain output gradient, dW rows of 147 columns (3*7*7, dw_cin) -- the stem's backward-
+    filter call; (96, 64, 64) is its row count at batch 24."""
+    from cunet_b200 import lib
+    lib.load()
+    cs = make_case(lib, lib.BF16, n, h, w, [128, 32], [0, 0], 128, 1, "plain", None)
+    dw = torch.zeros(128, 147, device=cs["dev"])
+    p = lib.ConvWgradParams()
+    fill_concat(p.inp, cs["srcs"], cs["stats"], cs["counts"], [0, 0], cs["gamma"], cs["beta"], cs["gamma"],
+                cs["gamma"], True)
+    p.inp.bn_train = 2
+    fill_grad_src(p.dy, cs, "plain")
+    p.N, p.H, p.W, p.taps, p.Cout = n, h, w, 1, 128
+    p.dw, p.nsplit, p.dtype, p.dw_cin = dw.data_ptr(), 0, lib.BF16, 147
+    lib.conv_wgrad(p)
+    torch.cuda.synchronize()
+    x = torch.cat([t.float() for t in cs["srcs"]], 1)            # [rows][160]
+    ref = (cs["g"].float().t() @ x)[:, :147]                     # dW[co][k] = sum_px dY[px][co] * x[px][k]
+    assert _relerr(dw, ref) < 2e-2

@@ -28,7 +28,7 @@ def fill_concat(cc, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train, a
 
 
 def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=True, out_fp32=False,
-                 cout_pad=None, seed=0, act_bits=0):
+                 cout_pad=None, seed=0, act_bits=0, identity=False):
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(seed)
     td = _mk(lib, dtype)
@@ -63,6 +63,8 @@ def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=
 
     p = lib.ConvFwdParams()
     fill_concat(p.inp, srcs, stats, counts, ups, gamma, beta, rmean, rvar, train, act_bits)
+    if identity:
+        p.inp.bn_train = 2
     p.N, p.H, p.W, p.taps = n, h, w, taps
     p.wpack, p.Cout, p.CoutPad = wpack.data_ptr(), cout, cout_pad
     p.out, p.out_ld, p.out_fp32 = out.data_ptr(), out_ld, int(out_fp32)
@@ -83,7 +85,7 @@ def run_conv_fwd(lib, dtype, n, h, w, seg_c, ups, cout, taps, pool=False, train=
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     ref, ridx = ops_ref.conv_fwd_ref([s.float() for s in srcs], ups, n, h, w, scale, shift, weight, pool,
-                                     act_bits=act_bits)
+                                     act_bits=act_bits, identity=identity)
     return out, ref, out_stats, pidx, ridx
 
 
@@ -248,3 +250,17 @@ def test_conv_fwd_quantized_activations(case, dtype_name):
     tol = (4e-3 if dtype == lib.F32 else 2.5e-2) * (2 if bits < 8 else 1)
     assert err < tol, "%s %s rel err %g" % (name, dtype_name, err)
     assert _relerr(plain.float()[:, :cout], ref) > 3 * err, "quantization had no effect?"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,h,w", [(8, 64, 64), (3, 16, 16), (96, 64, 64)])
+def test_conv_fwd_identity_input(n, h, w):
+    """conv0 over the im2col blocks (cunet_stem_im2col: two dense column blocks of 128 and 32 channels, bn_train == 2: no
+    BatchNorm, no ReLU) through the persistent 1x1 kernel; (96, 64, 64) is the row count of the stem at batch 24."""
+    from cunet_b200 import lib
+    lib.load()
+    out, ref, out_stats, _, _ = run_conv_fwd(lib, lib.BF16, n, h, w, [128, 32], [0, 0], 128, 1, identity=True)
+    assert torch.isfinite(out.float()).all()
+    assert _relerr(out.float(), ref) < 2e-2
+    # statistics of the stored (rounded) outputs, as every conv reports them
+    assert _relerr(out_stats, ops_ref.tensor_stats(out)) < 1e-4
