@@ -15,6 +15,7 @@ timeout 400 python bench.py --impl reference --steps 3 --warmup 3 > $O/bench_cun
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(conv_|stem_|mse_|decode_|pack_|rmsprop|bn_|quant_)' \
    --launch-skip ${SKIP:-1200} --launch-count ${COUNT:-1300} --csv --log-file $O/launches_cunet8_eager.csv \
    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-loss-check > $O/launches_run.log 2>&1
+python tools/launch_summary.py $O/launches_cunet8_eager.csv $O/launches_cunet8_eager_onestep.csv > $O/launches_summary.txt 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:conv_bwd1x1 --launch-skip 4 --launch-count 1 -f \
    -o $O/ncu_r2_bwd1x1_320up64 python tools/time_bwd1x1.py 320up64 > $O/ncu_bwd1x1.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:conv_fwd_v3 --launch-skip 4 --launch-count 1 -f \
