@@ -591,6 +591,12 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       gcf.mu = *reinterpret_cast<const uint4*>(&tail->gmu2[co2]);
       gcf.d = *reinterpret_cast<const uint4*>(&tail->gd2[co2]);
     }
+    // 32-bit shared-space bases, opaque to the compiler (it otherwise rebuilds the aligned base and the thread index at
+    // every use -- a dozen uniform-datapath instructions each time -- and reads the tables with generic loads)
+    uint32_t tr_sbase = smem_u32(smem);
+    uint32_t tr_coef = smem_u32(tail) + (uint32_t)offsetof(F1Tail, sc2) + (uint32_t)cc * 16u;   // + 256 B per chunk
+    uint32_t tr_stoff = (uint32_t)(cc >> 3) * F1_SUB + tile_off(rb, cc & 7);   // rows rb + 24 q: + q * 24 * 128 bytes
+    asm volatile("" : "+r"(tr_sbase), "+r"(tr_coef), "+r"(tr_stoff));
     const int relu_on = p.in.bn_train == 2 ? 0 : 1;
     ActCoef<bf16> acf_q;              // QuanInput constants (cunet_concat.act_bits), computed once
     acf_q.set_quant(p.in.act_bits);
@@ -642,20 +648,22 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
       if (t == 0 && i < 12) CUNET_TRACE_MARK(trace, 34 + 4 * i);
       // ---- activation operand per chunk -> A slots
       mbar_wait(&tail->x_full[b], upar);
-      const uint32_t xb = smem_u32(smem + L.x_off + b * L.x_bytes);
+      const uint32_t xb = tr_sbase + (uint32_t)(L.x_off + (int)b * L.x_bytes);
+      const bool v0 = rb < nv, v1 = rb + 24 < nv, v2 = rb + 48 < nv;   // this thread's three rows inside the stage
       // NOT unrolled over the chunks: unrolling tripled the code of this role (and of the epilogue below); the kernel
       // was 198 KB of SASS and its top stall reason in ncu was "no instruction" (instruction-cache misses).  The
       // per-chunk constants rotate through three registers instead of being indexed by a compile-time chunk number.
+      // The loop is written for the fewest instructions per warp: this role executes ~10 clocks per instruction (ncu:
+      // 183 SASS instructions and 1 us per chunk), every address is a 32-bit shared-space register + immediate, loads
+      // are unconditional (an invalid row reads in-range garbage that is replaced by zero), nothing branches.
 #pragma unroll 1
       for (int c = 0; c < nchunk; ++c) {
         ActCoef<bf16> acf;
-        acf.sc = *reinterpret_cast<const uint4*>(&tail->sc2[(c * 128 + cc * 8) >> 1]);
-        acf.sh = *reinterpret_cast<const uint4*>(&tail->sh2[(c * 128 + cc * 8) >> 1]);
+        acf.sc = f1_lds128(tr_coef + (uint32_t)c * 256u);
+        acf.sh = f1_lds128(tr_coef + (uint32_t)(offsetof(F1Tail, sh2) - offsetof(F1Tail, sc2)) + (uint32_t)c * 256u);
         acf.relu = relu_on;
         acf.qmax2 = acf_q.qmax2;
         acf.magic2 = acf_q.magic2;
-        mbar_wait(&tail->a_free[slot], sph ^ 1u);
-        const uint32_t abase = ab + slot * 16384u;
         const uint32_t pk = cs_pk[0];
         {                                     // rotate: the next chunk's word moves to the front
           const uint32_t t0 = cs_pk[0];
@@ -665,21 +673,17 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv_bwd1x1_kernel(const __grid
         const bool cvalid = (pk & 0x80000000u) != 0u, cup = (pk & 0x40000000u) != 0u;
         const uint32_t rx = xb + (pk & 0xFFFFu);
         const uint32_t lsh = 6u + ((pk >> 16) & 3u);      // log2(bytes per source row)
-        uint4 raw[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int r = rb + 24 * q;
-          raw[q] = make_uint4(0, 0, 0, 0);
-          if (cvalid && r < nv) raw[q] = f1_lds128(rx + ((uint32_t)(cup ? lowr[q] : r) << lsh));
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int r = rb + 24 * q;
-          if (r >= F1_R) break;
-          uint4 o = make_uint4(0, 0, 0, 0), lo_unused;
-          if (cvalid && r < nv) o = acf.apply(raw[q], lo_unused);
-          sts128(abase + (uint32_t)(cc >> 3) * F1_SUB + tile_off(r, cc & 7), o);
-        }
+        const uint4 raw0 = f1_lds128(rx + ((uint32_t)(cup ? lowr[0] : rb) << lsh));
+        const uint4 raw1 = f1_lds128(rx + ((uint32_t)(cup ? lowr[1] : rb + 24) << lsh));
+        const uint4 raw2 = f1_lds128(rx + ((uint32_t)(cup ? lowr[2] : min(rb + 48, F1_R - 1)) << lsh));
+        mbar_wait(&tail->a_free[slot], sph ^ 1u);
+        const uint32_t abase = tr_sbase + (uint32_t)L.a_off + slot * 16384u + tr_stoff;
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        uint4 lo_unused;
+        const uint4 o0 = acf.apply(raw0, lo_unused), o1 = acf.apply(raw1, lo_unused), o2 = acf.apply(raw2, lo_unused);
+        sts128(abase, (cvalid && v0) ? o0 : zero4);
+        sts128(abase + 24u * 128u, (cvalid && v1) ? o1 : zero4);
+        if (rb + 48 < F1_R) sts128(abase + 48u * 128u, (cvalid && v2) ? o2 : zero4);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
