@@ -153,7 +153,7 @@ def oracle_loss_main(cfg, batch):
     img, hm = synthetic.make_inputs(batch, cfg["class_num"], seed=0)
     with torch.no_grad():
         loss = cunet_oracle.multi_loss_mse(net(img), hm)
-    print(json.dumps(dict(loss_oracle=float(loss))))
+    _emit(dict(loss_oracle=float(loss)))
     return 0
 
 
@@ -179,6 +179,19 @@ def op_bytes(eng, op, kind):
     return src + dy + gacc
 
 
+_OUT_FD = None
+
+
+def _emit(obj):
+    """The record line, on the process's original stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +210,12 @@ def main():
     ap.add_argument("--no-loss-check", action="store_true", help="skip the CPU-oracle loss of the first step")
     ap.add_argument("--oracle-loss", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: anything a library prints there (NCCL writes its version banner
+    # to stdout at communicator creation) is sent to stderr instead
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
     cfg = dict(CONFIGS[args.config])
     if args.batch:
         cfg["batch"] = args.batch
@@ -223,7 +242,7 @@ def main():
         if rank != 0:
             return 0
         if cfg.get("quant"):
-            print(json.dumps(dict(impl="reference", unavailable="the CPU reference arm times the full-precision step only")))
+            _emit(dict(impl="reference", unavailable="the CPU reference arm times the full-precision step only"))
             return 0
         ips, cores = cpu_reference(cfg, args.cpu_sample, max(1, min(args.steps, 3)))
         ref_workload = ("CU-Net-%d order %d loss %d, %d classes, 256x256 -> 64x64 heatmaps, train step on the host CPU: "
@@ -238,7 +257,7 @@ def main():
                                       sample="%d-image training step (fwd+MSE+bwd+RMSprop) of the same model, median of %d"
                                              % (args.cpu_sample, max(1, min(args.steps, 3)))),
                     e2e=dict(value=ips, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -482,7 +501,7 @@ def main():
         except Exception as exc:  # noqa: BLE001 -- report, never fail the GPU line because of the CPU baseline
             line["cpu_baseline"] = dict(value=None, unit="images/s", cores=None, kind="port",
                                         sample="unavailable: %s" % type(exc).__name__)
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
