@@ -34,3 +34,22 @@ def test_reference_arm_other_ranks_and_quantized_config():
     assert out.returncode == 0 and out.stdout.strip() == ""          # only rank 0 runs and prints
     line = _run("--config", "cunet8bin")
     assert line["impl"] == "reference" and "unavailable" in line
+
+
+def test_reference_arm_stdout_is_one_line():
+    """stdout carries exactly the record (bench.py sends everything else, e.g. NCCL's version banner, to stderr)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cunet2",
+                          "--steps", "1", "--cpu-sample", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 1 and lines[0].startswith("{")
+
+
+def test_traffic_key_matches_the_kernel_source():
+    """bench.py reports `roofline.traffic` only while profiles/traffic.json is keyed to the sha1 of the dominant kernel's
+    source; a kernel edit without a fresh `ncu --set full` capture must show up here, not as a silent null in the line."""
+    import hashlib
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["conv_bwd1x1"]
+    src = os.path.join(ROOT, "cu-net_b200", "csrc", tj["kernel_file"])
+    assert hashlib.sha1(open(src, "rb").read()).hexdigest() == tj["kernel_sha1"]
+    assert 0.9 * 138412032 < tj["bytes"] < 1.3 * 138412032      # close to the op's algorithmic bytes (DESIGN.md section 3)
