@@ -78,3 +78,48 @@ def test_shard_batch_semantics():
     assert parallel.shard_batch(24, 3, 8, weak=True) == (72, 24)
     with pytest.raises(ValueError):
         parallel.shard_batch(24, 0, 5)
+
+
+def _worker_sharded(rank, world, port, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(7)
+    params = torch.randn(n, generator=g, dtype=torch.float64)          # identical replicas
+    sq = torch.rand(n, generator=g, dtype=torch.float64)
+    grads = torch.randn(n, generator=torch.Generator().manual_seed(100 + rank), dtype=torch.float64) / world
+    lr = 2.5e-4
+
+    # (a) allreduce + replicated RMSprop (the reference's DataParallel semantics)
+    ga = parallel.allreduce_mean(grads.clone(), world)
+    pa, sa = params.clone(), sq.clone()
+    cunet_oracle.rmsprop_step([pa], [ga], [sa], lr)
+
+    # (b) reduce-scatter -> RMSprop on this rank's slice only -> all-gather of the updated parameters
+    s, e = parallel.shard_range(n, rank, world)
+    gs = torch.empty(e - s, dtype=torch.float64)
+    parallel.reduce_scatter_mean(grads.clone(), gs, world)
+    assert torch.equal(gs, ga[s:e])                                     # the slice of the summed bucket, exactly
+    pb, sb = params.clone(), sq.clone()
+    shard_p, shard_s = pb[s:e].clone(), sb[s:e].clone()
+    cunet_oracle.rmsprop_step([shard_p], [gs], [shard_s], lr)
+    parallel.all_gather_params(pb, shard_p, world)
+    ok = torch.equal(pb, pa) and torch.equal(shard_s, sa[s:e])
+    flag = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        torch.save(dict(ok=bool(flag.item()), p=pb), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_optimizer_exchange_equals_allreduce(tmp_path):
+    """SURVEY.md section 8(f)1 host logic: reduce-scatter -> shard update -> all-gather leaves every rank with
+    bit-identical parameters to allreduce + replicated RMSprop (elementwise optimizer, same summed gradients)."""
+    out = str(tmp_path / "s.pt")
+    mp.spawn(_worker_sharded, args=(2, _free_port(), 4096, out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]
+    with pytest.raises(ValueError):
+        parallel.shard_range(4097, 0, 2)
+    assert parallel.shard_range(4096, 1, 2) == (2048, 4096)
